@@ -1,0 +1,130 @@
+// Kernel B: CMVN (extension) + SpecAug (src/blocks/sp_layers.py:51-74) in place
+// on the [B, T, Dm] feature tensor kernel A just wrote (5-8 MB: L2 resident on B200).
+//
+// SpecAug closed form.  The reference computes freq_means[b,t] = mean_d x and
+// time_means[b,d] = sum_t x / len ONCE from the un-masked input (:52-54), applies all
+// frequency masks (:58-64) and then all time masks (:67-73), so the final value is
+//     time-masked(t)  ->  time_means[b,d]
+//     freq-masked(d)  ->  freq_means[b,t]
+//     otherwise       ->  x[b,t,d]
+// Mask rectangles arrive as host-drawn integers (start, end) already resolved with Python
+// slice semantics (negative starts, spill into padding rows), so placement is bit-exact.
+#include "spl_internal.cuh"
+
+namespace spl {
+
+constexpr int kPostRows = 32;  // rows of one utterance per CTA
+constexpr int kPostThreads = 256;
+
+__global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) {
+  __shared__ float s_mean[kMaxDm], s_istd[kMaxDm], s_tm[kMaxDm];
+  __shared__ int s_mask[2 * kMaxMasks];
+  const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int Dm = p.Dm;
+  const int len = (int)p.feat_len[b];
+  const int nmask = p.mask_params ? (p.n_freq + p.n_time) : 0;
+
+  for (int d = tid; d < Dm; d += kPostThreads) {
+    float mean = 0.f, istd = 1.f, tm = 0.f;
+    double s1 = 0.0, s2 = 0.0;
+    if (p.utt_stats) {
+      s1 = p.utt_stats[((size_t)b * 2 + 0) * Dm + d];
+      s2 = p.utt_stats[((size_t)b * 2 + 1) * Dm + d];
+    }
+    const double inv_len = len > 0 ? 1.0 / (double)len : 0.0;
+    const double umean = s1 * inv_len;
+    if (p.cmvn_mode == SPL_CMVN_UTTERANCE) {
+      double var = s2 * inv_len - umean * umean;
+      var = var < 1e-20 ? 1e-20 : var;
+      mean = (float)umean;
+      istd = p.norm_vars ? (float)(1.0 / sqrt(var)) : 1.f;
+    } else if (p.cmvn_mode == SPL_CMVN_GLOBAL) {
+      mean = p.global_mean[d];
+      istd = p.norm_vars ? p.global_istd[d] : 1.f;
+    }
+    // time mean of the normalised features: (sum_t x / len - mean) * istd
+    tm = (float)((umean - (double)mean) * (double)istd);
+    s_mean[d] = mean;
+    s_istd[d] = istd;
+    s_tm[d] = tm;
+  }
+  for (int i = tid; i < 2 * nmask; i += kPostThreads)
+    s_mask[i] = p.mask_params[(size_t)b * 2 * nmask + i];
+  __syncthreads();
+
+  const int tend = min(t0 + kPostRows, p.T);
+  for (int t = t0 + w; t < tend; t += kPostThreads / 32) {
+    float* row = p.feats + ((size_t)b * p.T + t) * Dm;
+    bool tmask = false;
+    for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
+    if (tmask) {  // may legitimately touch padding rows (reference quirk for len < width)
+      for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
+      continue;
+    }
+    if (t >= len) continue;  // padding: stays exactly 0 (freq means of a zero row are 0)
+    float y[kMaxDm / 32];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxDm / 32; ++i) {
+      const int d = lane + 32 * i;
+      y[i] = 0.f;
+      if (d < Dm) {
+        y[i] = (row[d] - s_mean[d]) * s_istd[d];
+        sum += y[i];
+      }
+    }
+    float fm = 0.f;
+    if (p.n_freq > 0 && nmask > 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      fm = sum / (float)Dm;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxDm / 32; ++i) {
+      const int d = lane + 32 * i;
+      if (d < Dm) {
+        float v = y[i];
+        for (int j = 0; j < p.n_freq && j < nmask; ++j)
+          if (d >= s_mask[2 * j] && d < s_mask[2 * j + 1]) v = fm;
+        row[d] = v;
+      }
+    }
+  }
+}
+
+cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
+  dim3 grid((p.T + kPostRows - 1) / kPostRows, p.B);
+  post_kernel<<<grid, kPostThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// Column statistics over valid frames for the offline-feature path (sp_layers.py:92-99).
+__global__ void __launch_bounds__(256) column_stats_kernel(const float* __restrict__ feats,
+                                                           const int64_t* __restrict__ feat_len, int T, int Dm,
+                                                           double* __restrict__ utt_stats) {
+  const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
+  const int len = (int)feat_len[b];
+  const int tend = min(min(t0 + kPostRows, T), len);
+  for (int d = threadIdx.x; d < Dm; d += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int t = t0; t < tend; ++t) {
+      const float v = feats[((size_t)b * T + t) * Dm + d];
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+    if (tend > t0) {
+      atomicAdd(utt_stats + ((size_t)b * 2 + 0) * Dm + d, (double)s1);
+      atomicAdd(utt_stats + ((size_t)b * 2 + 1) * Dm + d, (double)s2);
+    }
+  }
+}
+
+cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
+                                double* utt_stats, cudaStream_t st) {
+  dim3 grid((T + kPostRows - 1) / kPostRows, B);
+  column_stats_kernel<<<grid, 256, 0, st>>>(feats, feat_len, T, Dm, utt_stats);
+  return cudaGetLastError();
+}
+
+}  // namespace spl

@@ -1,0 +1,272 @@
+// C-ABI of the B200 speech front-end: handle management, argument validation, launches.
+// See include/spl_capi.h for the contract and the reference interfaces each entry replaces.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "spl_internal.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return SPL_ERR_CUDA;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+struct spl_handle {
+  spl_config cfg;
+  int device;
+  int D_out;
+  void* blob;  // single device allocation holding every table
+  spl::Tables tab;
+  size_t smem_bytes;
+};
+
+extern "C" {
+
+int spl_abi_version(void) { return SPL_ABI_VERSION; }
+const char* spl_last_error(void) { return g_err.c_str(); }
+uint64_t spl_launch_count(void) { return g_launches.load(); }
+int spl_feature_dim(const spl_handle* h) { return h ? h->D_out : 0; }
+
+int spl_create(const spl_config* cfg, const float* window, const float* mel_dense, int device, spl_handle** out) {
+  if (!cfg || !window || !mel_dense || !out) return fail(SPL_ERR_INVALID_ARG, "spl_create: null argument");
+  if (cfg->abi_version != SPL_ABI_VERSION) return fail(SPL_ERR_INVALID_ARG, "spl_create: ABI version mismatch");
+  const int S = cfg->window_shift, Nw = cfg->window_size, nfft = cfg->padded_size, D = cfg->num_mel_bins;
+  if (nfft != 256 && nfft != 512)
+    return fail(SPL_ERR_UNSUPPORTED,
+                "spl_create: padded window must be 256 or 512 samples (sample rates ~5.2-20.4 kHz at 25 ms)");
+  if (Nw < 2 || Nw > nfft || 2 * Nw <= nfft) return fail(SPL_ERR_INVALID_ARG, "spl_create: window_size/padded_size");
+  if (S < 1 || S > Nw) return fail(SPL_ERR_INVALID_ARG, "spl_create: window_shift must be in [1, window_size]");
+  if (D < 4 || D > spl::kMaxMel) return fail(SPL_ERR_INVALID_ARG, "spl_create: num_mel_bins must be in [4, 128]");
+  if (!(cfg->preemph >= 0.f && cfg->preemph <= 1.f)) return fail(SPL_ERR_INVALID_ARG, "spl_create: preemph");
+
+  // ---- sparse mel bank (weights pre-scaled by 1/4: the kernel accumulates 4*|X|^2) ----
+  const int nb = nfft / 2;
+  std::vector<int32_t> lo(D), cnt(D), off(D);
+  std::vector<float> wts;
+  for (int m = 0; m < D; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < nb; ++k)
+      if (mel_dense[(size_t)m * nb + k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    lo[m] = first < 0 ? 0 : first;
+    cnt[m] = first < 0 ? 0 : last - first + 1;
+    off[m] = (int32_t)wts.size();
+    for (int i = 0; i < cnt[m]; ++i) wts.push_back(0.25f * mel_dense[(size_t)m * nb + lo[m] + i]);
+  }
+  const int nnz = (int)wts.size();
+  // filter groups for the 8 warps of the mel phase, balanced by (weights + per-filter overhead)
+  int32_t grp[spl::kWarps + 1];
+  {
+    std::vector<int> cost(D);
+    long total = 0;
+    for (int m = 0; m < D; ++m) total += (cost[m] = cnt[m] + 6);
+    int m = 0;
+    long acc = 0;
+    grp[0] = 0;
+    for (int w = 1; w < spl::kWarps; ++w) {
+      const long target = total * w / spl::kWarps;
+      while (m < D && acc + cost[m] / 2 < target) acc += cost[m++];
+      grp[w] = m;
+    }
+    grp[spl::kWarps] = D;
+  }
+  // stage-1 twiddles W_N^{n2 k1}
+  const int R2 = nfft / 16;
+  std::vector<float> twr(R2 * 16), twi(R2 * 16);
+  for (int n2 = 0; n2 < R2; ++n2)
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const double a = 2.0 * M_PI * (double)(n2 * k1) / (double)nfft;
+      twr[n2 * 16 + k1] = (float)std::cos(a);
+      twi[n2 * 16 + k1] = (float)std::sin(a);
+    }
+
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_create: cudaSetDevice failed");
+  // one blob: window | tw_re | tw_im | mel_w | lo | cnt | off   (all 4-byte items)
+  const size_t n_items = (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  std::vector<uint32_t> host(n_items);
+  size_t o = 0;
+  auto put = [&](const void* src, size_t n) {
+    std::memcpy(host.data() + o, src, n * 4);
+    size_t at = o;
+    o += n;
+    return at;
+  };
+  const size_t o_win = put(window, Nw), o_twr = put(twr.data(), twr.size()), o_twi = put(twi.data(), twi.size());
+  const float zero = 0.f;
+  const size_t o_w = nnz > 0 ? put(wts.data(), nnz) : put(&zero, 1);
+  const size_t o_lo = put(lo.data(), D), o_cnt = put(cnt.data(), D), o_off = put(off.data(), D);
+
+  void* blob = nullptr;
+  cudaError_t e = cudaMalloc(&blob, n_items * 4);
+  if (e != cudaSuccess) return fail_cuda(e, "spl_create: cudaMalloc");
+  e = cudaMemcpy(blob, host.data(), n_items * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(blob);
+    return fail_cuda(e, "spl_create: cudaMemcpy");
+  }
+  spl_handle* h = new spl_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->D_out = D + (cfg->use_energy ? 1 : 0);
+  h->blob = blob;
+  const float* fb = static_cast<const float*>(blob);
+  const int32_t* ib = static_cast<const int32_t*>(blob);
+  h->tab.window = fb + o_win;
+  h->tab.tw_re = fb + o_twr;
+  h->tab.tw_im = fb + o_twi;
+  h->tab.mel_w = fb + o_w;
+  h->tab.mel_lo = ib + o_lo;
+  h->tab.mel_cnt = ib + o_cnt;
+  h->tab.mel_off = ib + o_off;
+  h->tab.mel_nnz = nnz;
+  for (int w = 0; w <= spl::kWarps; ++w) h->tab.grp_beg[w] = grp[w];
+  h->smem_bytes = spl::fbank_smem_bytes(nfft, S, Nw, D, h->D_out, nnz);
+  if (h->smem_bytes > 113 * 1024) {  // two CTAs per SM must fit in 227 KB
+    cudaFree(blob);
+    delete h;
+    return fail(SPL_ERR_UNSUPPORTED, "spl_create: configuration needs too much shared memory");
+  }
+  *out = h;
+  return SPL_OK;
+}
+
+void spl_destroy(spl_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  cudaFree(h->blob);
+  delete h;
+}
+
+int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
+  if (!h || !a) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null argument");
+  if (!a->wav || !a->wav_len || !a->feats) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null buffer");
+  if (a->B < 1 || a->B > 65535 || a->T < 1) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: B/T out of range");
+  if (a->wav_pitch < h->cfg.window_size) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: wav_pitch < window");
+  if (a->sample_format != SPL_SAMPLES_F32 && a->sample_format != SPL_SAMPLES_I16)
+    return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: sample_format");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_fbank_forward: cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  spl::FbankParams p;
+  p.S = h->cfg.window_shift;
+  p.Nw = h->cfg.window_size;
+  p.D = h->cfg.num_mel_bins;
+  p.D_out = h->D_out;
+  p.use_energy = h->cfg.use_energy;
+  p.remove_dc = h->cfg.remove_dc;
+  p.preemph = h->cfg.preemph;
+  p.dither = h->cfg.dither;
+  p.wav = a->wav;
+  p.wav_pitch = a->wav_pitch;
+  p.sample_format = a->sample_format;
+  p.wav_len = a->wav_len;
+  p.B = a->B;
+  p.T = a->T;
+  p.feats = a->feats;
+  p.feat_len = a->feat_len;
+  p.noise = a->noise;
+  p.seed_lo = (uint32_t)(a->dither_seed & 0xffffffffu);
+  p.seed_hi = (uint32_t)(a->dither_seed >> 32);
+  p.utt_stats = a->utt_stats;
+  p.global_stats = a->global_stats;
+  p.tab = h->tab;
+
+  if (a->utt_stats) {
+    cudaError_t e = cudaMemsetAsync(a->utt_stats, 0, sizeof(double) * 2 * (size_t)a->B * h->D_out, st);
+    if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: cudaMemsetAsync");
+  }
+  const bool with_noise = h->cfg.dither != 0.f;
+  cudaError_t e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
+  if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
+}
+
+int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream) {
+  if (!a || !a->feats || !a->feat_len) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: null argument");
+  if (a->B < 1 || a->B > 65535 || a->T < 1 || a->Dm < 1 || a->Dm > spl::kMaxDm)
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: B/T/Dm out of range (Dm <= 160)");
+  const int nmask = a->mask_params ? a->n_freq_masks + a->n_time_masks : 0;
+  if (a->n_freq_masks < 0 || a->n_time_masks < 0 || nmask > spl::kMaxMasks)
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: at most 32 masks per utterance");
+  if (a->cmvn_mode == SPL_CMVN_UTTERANCE && !a->utt_stats)
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: utterance CMVN needs utt_stats");
+  if (a->cmvn_mode == SPL_CMVN_GLOBAL && (!a->global_mean || (a->norm_vars && !a->global_istd)))
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: global CMVN needs global_mean/global_istd");
+  if (a->mask_params && a->n_time_masks > 0 && !a->utt_stats)
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: time masks need utt_stats (time means)");
+  if (a->cmvn_mode == SPL_CMVN_NONE && nmask == 0) return SPL_OK;  // nothing to do
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  DeviceGuard guard(h ? h->device : cur_dev);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_post_inplace: cudaSetDevice failed");
+  spl::PostParams p;
+  p.feats = a->feats;
+  p.feat_len = a->feat_len;
+  p.B = a->B;
+  p.T = a->T;
+  p.Dm = a->Dm;
+  p.cmvn_mode = a->cmvn_mode;
+  p.norm_vars = a->norm_vars;
+  p.utt_stats = a->utt_stats;
+  p.global_mean = a->global_mean;
+  p.global_istd = a->global_istd;
+  p.n_freq = a->mask_params ? a->n_freq_masks : 0;
+  p.n_time = a->mask_params ? a->n_time_masks : 0;
+  p.mask_params = a->mask_params;
+  cudaError_t e = spl::launch_post(p, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "spl_post_inplace: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
+}
+
+int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len, int32_t B, int32_t T, int32_t Dm,
+                     double* utt_stats, void* stream) {
+  if (!feats || !feat_len || !utt_stats) return fail(SPL_ERR_INVALID_ARG, "spl_column_stats: null argument");
+  if (B < 1 || B > 65535 || T < 1 || Dm < 1) return fail(SPL_ERR_INVALID_ARG, "spl_column_stats: B/T/Dm out of range");
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  DeviceGuard guard(h ? h->device : cur_dev);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_column_stats: cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(utt_stats, 0, sizeof(double) * 2 * (size_t)B * Dm, st);
+  if (e != cudaSuccess) return fail_cuda(e, "spl_column_stats: cudaMemsetAsync");
+  e = spl::launch_column_stats(feats, feat_len, B, T, Dm, utt_stats, st);
+  if (e != cudaSuccess) return fail_cuda(e, "spl_column_stats: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
+}
+
+}  // extern "C"

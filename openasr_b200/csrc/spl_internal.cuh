@@ -1,0 +1,69 @@
+// Internal declarations shared by the C-ABI translation unit and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spl_capi.h"
+
+namespace spl {
+
+constexpr int kTileFrames = 32;   // frames per CTA tile (8 warps x 4 frames)
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxMel = 128;
+constexpr int kMaxDm = 160;     // widest feature row kernel B handles (offline features included)
+constexpr int kMaxMasks = 32;   // freq + time masks per utterance
+constexpr float kEps = 1.1920928955078125e-07f;  // kaldi_signal.py:48
+
+// Device-resident constant tables of one handle.
+struct Tables {
+  const float* window;     // [Nw]
+  const float* tw_re;      // [R2 * 16] stage-1 twiddles cos(2 pi n2 k1 / Nfft)
+  const float* tw_im;      // [R2 * 16] sin(2 pi n2 k1 / Nfft)
+  const float* mel_w;      // [nnz] packed non-zero mel weights (already scaled by 1/4, see kernel)
+  const int32_t* mel_lo;   // [D] first FFT bin of filter
+  const int32_t* mel_cnt;  // [D] number of bins
+  const int32_t* mel_off;  // [D] offset into mel_w
+  int32_t mel_nnz;
+  int32_t grp_beg[kWarps + 1];  // filters [grp_beg[w], grp_beg[w+1]) handled by warp w in the mel phase
+};
+
+struct FbankParams {
+  // config
+  int32_t S, Nw, D, D_out, use_energy, remove_dc;
+  float preemph, dither;
+  // call
+  const void* wav;
+  int64_t wav_pitch;
+  int32_t sample_format;
+  const int64_t* wav_len;
+  int32_t B, T;
+  float* feats;
+  int64_t* feat_len;
+  const float* noise;
+  uint32_t seed_lo, seed_hi;
+  double* utt_stats;
+  double* global_stats;
+  Tables tab;
+};
+
+struct PostParams {
+  float* feats;
+  const int64_t* feat_len;
+  int32_t B, T, Dm;
+  int32_t cmvn_mode, norm_vars;
+  const double* utt_stats;
+  const float* global_mean;
+  const float* global_istd;
+  int32_t n_freq, n_time;
+  const int32_t* mask_params;
+};
+
+// host-side launchers (defined in the .cu files); return cudaError_t of the launch
+cudaError_t launch_fbank(const FbankParams& p, int nfft, bool with_noise, cudaStream_t st);
+size_t fbank_smem_bytes(int nfft, int S, int Nw, int D, int D_out, int nnz);
+cudaError_t launch_post(const PostParams& p, cudaStream_t st);
+cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
+                                double* utt_stats, cudaStream_t st);
+
+}  // namespace spl

@@ -1,0 +1,263 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed reference vectors
+and against the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): log-mel max-abs 1e-3 and |d| <= 1e-3 + 1e-4*|ref| in fp32;
+frame counts / lengths / mask rectangles / zero padding exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-3, 1e-4
+
+
+def close(a, b):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = (a - b).abs()
+    assert torch.isfinite(a).all()
+    ok = d <= ATOL + RTOL * b.abs()
+    assert ok.all(), "max|d|=%g at %s" % (d.max().item(), np.unravel_index(int(d.argmax()), tuple(d.shape)))
+    return d.max().item()
+
+
+def make_layer(**kw):
+    from openasr_b200 import SPLayer
+    conf = {"feature_type": "fbank", "sample_rate": 16000, "num_mel_bins": 80, "use_energy": False, "dither": 0.0}
+    conf.update(kw)
+    return SPLayer(conf).cuda(), conf
+
+
+def pad_batch(ws):
+    lens = [w.shape[0] for w in ws]
+    x = torch.zeros(len(ws), max(lens))
+    for i, w in enumerate(ws):
+        x[i, :lens[i]] += w
+    return x, lens
+
+
+# ---------------------------------------------------------------------------------------------
+GOLDEN_CASES = {
+    "w0_d80": (0, 16000, 1, 80, False, "povey"),
+    "w1_d80": (1, 16000, 1, 80, False, "povey"),
+    "w0_d40": (0, 16000, 1, 40, False, "povey"),
+    "w1_d40": (1, 16000, 1, 40, False, "povey"),
+    "w0_d80_energy": (0, 16000, 1, 80, True, "povey"),
+    "w1_d80_hamming": (1, 16000, 1, 80, False, "hamming"),
+    "w1_8k_d40": (1, 8000, 2, 40, False, "povey"),
+}
+
+
+@pytest.mark.parametrize("key", sorted(GOLDEN_CASES))
+def test_fbank_matches_reference_vectors(key, wavs, golden_dir):
+    wi, sr, dec, D, en, wt = GOLDEN_CASES[key]
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, "fbank_ref.npz"))[key])
+    layer, _ = make_layer(sample_rate=sr, num_mel_bins=D, use_energy=en, window_type=wt)
+    layer.eval()
+    w = wavs[wi][::dec].contiguous()
+    feats, flen = layer(w.view(1, -1).cuda(), [w.shape[0]])
+    assert flen.dtype == torch.int64 and flen.tolist() == [ref.shape[0]]
+    assert feats.shape == (1,) + tuple(ref.shape)
+    close(feats[0], ref)
+
+
+def test_known_answers(wavs, golden_dir):
+    ka = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    layer, _ = make_layer()
+    layer.eval()
+    f, _ = layer(wavs[0].view(1, -1).cuda(), [wavs[0].shape[0]])
+    k = ka["w0_d80"]
+    assert list(f.shape[1:]) == k["shape"]
+    assert abs(f[0, 0, 0].item() - k["first"]) < 1e-3
+    assert abs(f[0, 100, 40].item() - k["mid"]) < 1e-3
+    assert abs(f[0, -1, -1].item() - k["last"]) < 1e-3
+    assert abs(f.double().sum().item() - k["sum"]) < 1e-3 * f.numel() * 0.05
+    # all-zero input: every frame is log(eps)
+    for n, m in ((400, 1), (559, 1), (560, 2)):
+        z, zl = layer(torch.zeros(1, n).cuda(), [n])
+        assert zl.tolist() == [m] and z.shape == (1, m, 80)
+        assert torch.allclose(z.cpu(), torch.full((1, m, 80), ka["zeros_%d" % n]["first"]), atol=1e-5)
+
+
+def test_c1_fixture_batch_ragged_padding(wavs):
+    """BASELINE configs[0]: batch 4 = [w0, w1, w0, w1], 80-dim, vs the oracle; padding exactly 0."""
+    layer, conf = make_layer()
+    layer.eval()
+    x, lens = pad_batch([wavs[0], wavs[1], wavs[0], wavs[1]])
+    feats, flen = layer(x.cuda(), torch.tensor(lens).cuda())
+    ref, rlen = fo.splayer_forward(x, lens, conf)
+    assert torch.equal(flen.cpu(), rlen)
+    assert flen.device.type == "cuda"
+    close(feats, ref)
+    for i, m in enumerate(rlen.tolist()):
+        assert (feats[i, m:] == 0).all()
+
+
+def test_int16_ingest_equals_fp32(wavs):
+    layer, _ = make_layer()
+    layer.eval()
+    x, lens = pad_batch([wavs[0], wavs[1]])
+    a, _ = layer(x.cuda(), lens)
+    b, _ = layer(x.to(torch.int16).cuda(), lens)
+    assert torch.equal(a, b)
+
+
+def test_host_dither_stream_parity(wavs, golden_dir):
+    """dither=1 with the reference's exact CPU noise stream (seeded) against the reference vectors."""
+    g = np.load(os.path.join(golden_dir, "fbank_ref.npz"))
+    layer, _ = make_layer(dither=1.0, dither_rng="host")
+    layer.eval()
+    torch.manual_seed(7)
+    f, _ = layer(wavs[0].view(1, -1).cuda(), [wavs[0].shape[0]])
+    close(f[0], torch.from_numpy(g["w0_d80_dither_seed7"]))
+    layer8, _ = make_layer(dither=1.0, dither_rng="host", sample_rate=8000, num_mel_bins=40, use_energy=True)
+    layer8.eval()
+    w = wavs[1][::2].contiguous()
+    torch.manual_seed(11)
+    f, _ = layer8(w.view(1, -1).cuda(), [w.shape[0]])
+    close(f[0], torch.from_numpy(g["w1_8k_d40_energy_dither_seed11"]))
+
+
+def test_host_dither_batch_order(wavs):
+    """Batch of two: noise is consumed per utterance in batch order, like the reference loop."""
+    layer, conf = make_layer(dither=1.0, dither_rng="host")
+    layer.eval()
+    x, lens = pad_batch([wavs[1], wavs[0]])
+    torch.manual_seed(21)
+    f, _ = layer(x.cuda(), lens)
+    torch.manual_seed(21)
+    ref, _ = fo.splayer_forward(x, lens, conf)
+    close(f, ref)
+
+
+def test_device_dither_statistics():
+    """Throughput-mode dither: same distribution (mean 0.057, std 1.057 of the one-uniform
+    pseudo Box-Muller), deterministic per seed, different across seeds.  On an all-zero input
+    the features are a pure function of the noise, so compare their statistics with the oracle's."""
+    layer, conf = make_layer(dither=1.0, dither_rng="device")
+    layer.eval()
+    x = torch.zeros(8, 16000 * 6)
+    lens = [x.shape[1]] * 8
+    torch.manual_seed(5)
+    a, _ = layer(x.cuda(), lens)
+    torch.manual_seed(5)
+    b, _ = layer(x.cuda(), lens)
+    torch.manual_seed(6)
+    c, _ = layer(x.cuda(), lens)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    torch.manual_seed(0)
+    ref, _ = fo.splayer_forward(x, lens, dict(conf))
+    am, rm = a.cpu().mean(dim=(0, 1)), ref.mean(dim=(0, 1))
+    assert (am - rm).abs().max() < 0.12, (am - rm).abs().max()  # ~4 sigma of a one-bin filter mean
+    asd, rsd = a.cpu().std(dim=(0, 1)), ref.std(dim=(0, 1))
+    assert ((asd - rsd).abs() / rsd).max() < 0.15
+
+
+@pytest.mark.parametrize("sr,D,B,lo,hi", [(16000, 80, 32, 56000, 104000), (8000, 40, 64, 16000, 48000),
+                                          (16000, 80, 16, 192000, 320000)])
+def test_synthetic_shapes_vs_oracle(sr, D, B, lo, hi):
+    """BASELINE configs[1..3] at a batch the oracle finishes in seconds (B/4 utterances)."""
+    layer, conf = make_layer(sample_rate=sr, num_mel_bins=D)
+    layer.eval()
+    x, lens = fo.synth_batch(max(2, B // 4), lo, hi, sr, seed=1234)
+    feats, flen = layer(x.cuda(), lens)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
+    assert torch.equal(flen.cpu(), rlen)
+    close(feats, ref)
+
+
+def test_cmvn_utterance_vs_fp64_oracle(wavs):
+    layer, conf = make_layer(cmvn="utterance")
+    layer.eval()
+    x, lens = pad_batch([wavs[0], wavs[1], wavs[0][:9000]])
+    feats, flen = layer(x.cuda(), lens)
+    ref, rlen = fo.splayer_forward(x, lens, conf)
+    assert torch.equal(flen.cpu(), rlen)
+    close(feats, ref)
+    for i, m in enumerate(rlen.tolist()):
+        assert (feats[i, m:] == 0).all()
+        assert feats[i, :m].mean(0).abs().max() < 1e-4
+    layer2, conf2 = make_layer(cmvn="utterance", cmvn_norm_vars=False)
+    layer2.eval()
+    f2, _ = layer2(x.cuda(), lens)
+    close(f2, fo.splayer_forward(x, lens, conf2)[0])
+
+
+def test_specaug_rectangles_bit_exact(wavs, golden_dir):
+    """SpecAug on the offline path against the reference's own spec_aug output (seed 0 / seed 3)."""
+    from openasr_b200 import SPLayer
+    g = np.load(os.path.join(golden_dir, "fbank_ref.npz"))
+    s = np.load(os.path.join(golden_dir, "specaug_ref.npz"))
+    f0, f1 = torch.from_numpy(g["w0_d80"]), torch.from_numpy(g["w1_d80"])
+    pad = torch.zeros(2, 418, 80)
+    pad[0, :202] = f0
+    pad[1] = f1
+    lens = torch.from_numpy(s["lengths"])
+    for seed, key, sa in ((0, "aug_seed0", (2, 27, 2, 40)), (3, "aug2_seed3", (1, 15, 3, 300))):
+        conf = {"feature_type": "offline",
+                "spec_aug": dict(zip(("freq_mask_num", "freq_mask_width", "time_mask_num", "time_mask_width"), sa))}
+        layer = SPLayer(conf).train()
+        torch.manual_seed(seed)
+        x = pad.clone().cuda()
+        out, olen = layer(x, lens)
+        assert out.data_ptr() == x.data_ptr()  # in place, like the reference
+        ref = torch.from_numpy(s[key])
+        assert torch.equal(out.cpu() != pad, ref != pad), "mask rectangles differ"
+        close(out, ref)
+        assert torch.equal(olen.cpu(), lens)
+
+
+def test_full_training_forward_c2_like():
+    """fbank + utterance CMVN + SpecAug (training) vs the oracle with the same host uniforms."""
+    sa = {"freq_mask_num": 2, "freq_mask_width": 27, "time_mask_num": 2, "time_mask_width": 40}
+    layer, conf = make_layer(cmvn="utterance", spec_aug=sa)
+    layer.train()
+    x, lens = fo.synth_batch(6, 30000, 90000, 16000, seed=9)
+    torch.manual_seed(77)
+    feats, flen = layer(x.cuda(), lens)
+    torch.manual_seed(77)
+    uni = torch.rand(8, 6)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni)
+    assert torch.equal(flen.cpu(), rlen)
+    close(feats, ref)
+    # eval mode: no SpecAug
+    layer.eval()
+    e, _ = layer(x.cuda(), lens)
+    close(e, fo.splayer_forward(x, lens.tolist(), conf, training=False)[0])
+
+
+def test_short_time_mask_quirk():
+    """len < time_mask_width: negative starts / spill into padding follow Python slice rules."""
+    sa = {"freq_mask_num": 1, "freq_mask_width": 10, "time_mask_num": 2, "time_mask_width": 100}
+    layer, conf = make_layer(spec_aug=sa, num_mel_bins=40)
+    layer.train()
+    x, lens = fo.synth_batch(5, 4000, 30000, 16000, seed=2)
+    for seed in range(6):
+        torch.manual_seed(seed)
+        feats, flen = layer(x.cuda(), lens)
+        torch.manual_seed(seed)
+        uni = torch.rand(6, 5)
+        ref, _ = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni)
+        close(feats, ref)
+
+
+def test_errors_and_api():
+    from openasr_b200 import SPLayer, WavConv
+    with pytest.raises(ValueError):
+        SPLayer({"feature_type": "mfcc"})
+    layer, _ = make_layer()
+    with pytest.raises(AssertionError):
+        layer(torch.zeros(1, 399).cuda(), [399])
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(1, 1000), [1000])  # CPU tensor: no fallback
+    assert len(layer.state_dict()) == 0
+    wc = WavConv({"d_model": 8}).cuda()
+    y, ly = wc(torch.randn(2, 3200).cuda(), torch.tensor([3200, 1600]).cuda())
+    assert y.shape == (2, 20, 8) and ly.tolist() == [20, 10]

@@ -1,0 +1,140 @@
+"""CPU: host-side logic of the drop-in (tables, frame arithmetic, SpecAug rectangles, module API,
+C-ABI exports).  No compute calls -- there is no GPU here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_oracle as fo
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from openasr_b200 import _capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "spl_capi.h")).read()
+    declared = set(re.findall(r"SPL_API\s+[\w\s\*]+?\b(spl_\w+)\s*\(", hdr))
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    lib = _capi.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.spl_abi_version() == _capi.SPL_ABI_VERSION
+    assert ctypes.sizeof(_capi.SplConfig) == 36
+    # argument validation paths that need no device
+    assert lib.spl_fbank_forward(None, None, None) != 0
+    assert b"null" in lib.spl_last_error()
+
+
+def test_tables_bit_identical_to_oracle():
+    from openasr_b200 import tables
+    for sr in (16000.0, 8000.0, 11025.0):
+        S, Nw, Nfft = tables.frame_geometry(sr)
+        assert (S, Nw, Nfft) == fo.frame_params(sr)
+        for wt in tables.WINDOW_TYPES:
+            assert torch.equal(tables.window_table(wt, Nw), fo.window_function(wt, Nw))
+        for D in (23, 40, 80):
+            assert torch.equal(tables.mel_table(D, Nfft, sr), fo.mel_banks(D, Nfft, sr))
+    assert tables.frame_geometry(16000.0) == (160, 400, 512)
+    assert tables.frame_geometry(8000.0) == (80, 200, 256)
+    m = tables.mel_table(80, 512, 16000.0)
+    assert int((m != 0).sum()) == 501 and float(m[:, 0].abs().max()) == 0.0
+    assert int((tables.mel_table(40, 256, 8000.0) != 0).sum()) == 247
+    assert abs(float(tables.window_table("povey", 400).sum()) - 212.14699) < 1e-3
+
+
+def test_frame_count_matches_oracle():
+    from openasr_b200 import tables
+    for n in (399, 400, 559, 560, 561, 32640, 67263):
+        assert tables.frame_count(n, 400, 160) == fo.num_frames(n, 400, 160)
+    assert tables.frame_count(399, 400, 160) == 0 and tables.frame_count(560, 400, 160) == 2
+
+
+def test_specaug_rectangles_equal_reference_slicing():
+    """Closed form (rectangles + time/freq means) == the sequential in-place reference code,
+    including overlapping masks, negative starts and spills into padding."""
+    from openasr_b200 import frontend
+    g = torch.Generator().manual_seed(0)
+    B, T, V = 6, 90, 24
+    lens = torch.tensor([90, 3, 45, 60, 10, 77])
+    feats = torch.randn(B, T, V, generator=g)
+    for i, l in enumerate(lens.tolist()):
+        feats[i, l:] = 0
+    for trial, conf in enumerate(({"freq_mask_num": 2, "freq_mask_width": 10, "time_mask_num": 2, "time_mask_width": 40},
+                                  {"freq_mask_num": 1, "freq_mask_width": 30, "time_mask_num": 3, "time_mask_width": 120},
+                                  {"freq_mask_num": 0, "freq_mask_width": 5, "time_mask_num": 1, "time_mask_width": 8})):
+        for seed in range(20):
+            torch.manual_seed(100 * trial + seed)
+            uni = frontend.specaug_uniforms(B, conf["freq_mask_num"], conf["time_mask_num"])
+            ref, _ = fo.spec_aug(feats.clone(), lens, conf, uniforms=uni)
+            rect = frontend.specaug_rectangles(uni, lens, T, V, conf)
+            assert rect.shape == (B, conf["freq_mask_num"] + conf["time_mask_num"], 2) and rect.dtype == torch.int32
+            fm = feats.mean(-1)
+            tm = feats.sum(1) / lens[:, None].float()
+            out = feats.clone()
+            nf = conf["freq_mask_num"]
+            for b in range(B):
+                for j in range(nf):
+                    s, e = rect[b, j].tolist()
+                    out[b, :, s:e] = fm[b][:, None]
+                for j in range(nf, rect.shape[1]):
+                    s, e = rect[b, j].tolist()
+                    out[b, s:e, :] = tm[b][None, :]
+            assert torch.equal(out, ref)
+
+
+def test_specaug_uniform_stream_equals_sequential_draws():
+    from openasr_b200 import frontend
+    torch.manual_seed(4)
+    a = frontend.specaug_uniforms(7, 2, 2)
+    torch.manual_seed(4)
+    b = torch.stack([torch.rand(size=[7]) for _ in range(8)])
+    assert torch.equal(a, b)
+
+
+def test_splayer_module_contract():
+    from openasr_b200 import SPLayer, WavConv
+    from openasr_b200.blocks import sp_layers
+    conf = {"feature_type": "fbank", "sample_rate": 16000, "num_mel_bins": 80, "use_energy": False,
+            "spec_aug": {"freq_mask_num": 2, "freq_mask_width": 27, "time_mask_num": 2, "time_mask_width": 40}}
+    keys = dict(conf)
+    layer = SPLayer(conf)
+    assert layer.config is conf and conf == keys  # un-mutated (Speech_Models.restore compares key by key)
+    assert layer.feature_type == "fbank" and layer.spec_aug_conf == conf["spec_aug"]
+    assert len(layer.state_dict()) == 0 and len(list(layer.parameters())) == 0
+    layer.load_state_dict({}, strict=True)
+    assert SPLayer({"feature_type": "offline"}).spec_aug_conf is None
+    with pytest.raises(ValueError, match="Unknown feature type"):
+        SPLayer({"feature_type": "spectrogram"})
+    with pytest.raises(ValueError):
+        SPLayer({"feature_type": "fbank", "sample_rate": 16000, "num_mel_bins": 80, "use_energy": False, "cmvn": "x"})
+    # no CPU fallback: a CPU waveform is a hard error, never a silent slow path
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(torch.zeros(1, 16000), [16000])
+    # offline pass-through in eval mode needs no device
+    off = SPLayer({"feature_type": "offline"}).eval()
+    x = torch.randn(2, 5, 4)
+    y, l = off(x, torch.tensor([5, 3]))
+    assert y is x and l.dtype == torch.int64
+    assert hasattr(sp_layers, "WavConv")
+    names = [k for k in WavConv({"d_model": 4}).state_dict().keys() if k.endswith("weight")]
+    assert names[0] == "encoder.0.weight" and "encoder.12.weight" in names
+
+
+def test_wavconv_matches_reference_module():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference not mounted")
+    _, _ = ref_shim.load()
+    from blocks.sp_layers import WavConv as RefWavConv  # the reference's
+    from openasr_b200 import WavConv
+    torch.manual_seed(0)
+    ref = RefWavConv({"d_model": 16}).eval()
+    ours = WavConv({"d_model": 16}).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(2, 4800)
+    l = torch.tensor([4800, 3200])
+    a, la = ref(x, l)
+    b, lb = ours(x, l)
+    assert torch.equal(a, b) and torch.equal(la, lb)
