@@ -152,12 +152,12 @@ def build_pool(layer, conf, wl, pool, dev, seed):
     """Device-resident pool of distinct batches + everything a step needs (lengths, mask rectangles,
     output buffers), so the timed region holds only the hot-path launches."""
     from openasr_b200 import frontend, tables
-    from oracle import frontend_oracle as fo  # synthetic-input generator only (SURVEY 8d recipe)
+    from openasr_b200.synth import synth_batch
     B, lo, hi, sr, D, cmvn, sa = WORKLOADS[wl]
     h = layer._handle(dev)
     items = []
     for i in range(pool):
-        wav, lens = fo.synth_batch(B, lo, hi, sr, seed=seed + 7919 * i)
+        wav, lens = synth_batch(B, lo, hi, sr, seed=seed + 7919 * i)
         frames = [tables.frame_count(int(n), h.win, h.shift) for n in lens.tolist()]
         T = max(frames)
         it = {

@@ -76,7 +76,9 @@ SPL_API void spl_destroy(spl_handle* h);
 /* Per-call arguments of the fused fbank kernel (kernel A).  Device pointers unless noted. */
 typedef struct spl_fbank_args {
   const void* wav;         /* [B, wav_pitch] samples, int16-scaled; f32 or i16 per sample_format */
-  int64_t wav_pitch;       /* elements between utterance rows (>= max n_i) */
+  int64_t wav_pitch;       /* elements between utterance rows (>= wav_cols) */
+  int64_t wav_cols;        /* addressable elements per row (>= max n_i); the library never touches
+                              memory outside [wav, wav + (B-1)*wav_pitch + wav_cols) */
   int32_t sample_format;   /* spl_sample_format */
   const int64_t* wav_len;  /* [B] valid samples per utterance */
   int32_t B;

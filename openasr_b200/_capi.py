@@ -36,6 +36,7 @@ class SplFbankArgs(C.Structure):
     _fields_ = [
         ("wav", C.c_void_p),
         ("wav_pitch", C.c_int64),
+        ("wav_cols", C.c_int64),
         ("sample_format", C.c_int32),
         ("wav_len", C.c_void_p),
         ("B", C.c_int32),

@@ -78,35 +78,70 @@ SPL_HD void dif_bfly(float& ar, float& ai, float& br, float& bi) {
   }
 }
 
-template <int N, int SPAN, int BASE, int J>
+// Butterfly whose second input is known to be zero: (a, 0) -> (a, a * W_M^j).
+template <int M, int J>
+SPL_HD void dif_bfly_bzero(float ar, float ai, float& br, float& bi) {
+  if constexpr (J == 0) {
+    br = ar;
+    bi = ai;
+  } else if constexpr (4 * J == M) {
+    br = ai;
+    bi = -ar;
+  } else if constexpr (8 * J == M) {
+    constexpr float h = 0.70710678118654752440f;
+    br = (ar + ai) * h;
+    bi = (ai - ar) * h;
+  } else if constexpr (8 * J == 3 * M) {
+    constexpr float h = 0.70710678118654752440f;
+    br = (ai - ar) * h;
+    bi = -(ar + ai) * h;
+  } else {
+    constexpr float c = cos64(J * (64 / M));
+    constexpr float s = sin64(J * (64 / M));
+    br = ar * c + ai * s;
+    bi = ai * c - ar * s;
+  }
+}
+
+// NZ: inputs with index >= NZ are known to be zero (zero-padded frames); only the first
+// (widest) stage can exploit it, afterwards every slot is populated.
+template <int N, int SPAN, int BASE, int J, int NZ>
 struct DifStageJ {
   static SPL_HD void run(float (&re)[N], float (&im)[N]) {
-    dif_bfly<2 * SPAN, J>(re[BASE + J], im[BASE + J], re[BASE + J + SPAN], im[BASE + J + SPAN]);
-    if constexpr (J + 1 < SPAN) DifStageJ<N, SPAN, BASE, J + 1>::run(re, im);
+    if constexpr (2 * SPAN == N && BASE + J + SPAN >= NZ) {
+      static_assert(BASE + J < NZ || NZ == 0, "at least half of the inputs must be populated");
+      dif_bfly_bzero<2 * SPAN, J>(re[BASE + J], im[BASE + J], re[BASE + J + SPAN], im[BASE + J + SPAN]);
+    } else {
+      dif_bfly<2 * SPAN, J>(re[BASE + J], im[BASE + J], re[BASE + J + SPAN], im[BASE + J + SPAN]);
+    }
+    if constexpr (J + 1 < SPAN) DifStageJ<N, SPAN, BASE, J + 1, NZ>::run(re, im);
   }
 };
 
-template <int N, int SPAN, int BASE>
+template <int N, int SPAN, int BASE, int NZ>
 struct DifStageB {
   static SPL_HD void run(float (&re)[N], float (&im)[N]) {
-    DifStageJ<N, SPAN, BASE, 0>::run(re, im);
-    if constexpr (BASE + 2 * SPAN < N) DifStageB<N, SPAN, BASE + 2 * SPAN>::run(re, im);
+    DifStageJ<N, SPAN, BASE, 0, NZ>::run(re, im);
+    if constexpr (BASE + 2 * SPAN < N) DifStageB<N, SPAN, BASE + 2 * SPAN, NZ>::run(re, im);
   }
 };
 
-template <int N, int SPAN>
+template <int N, int SPAN, int NZ>
 struct DifAll {
   static SPL_HD void run(float (&re)[N], float (&im)[N]) {
-    DifStageB<N, SPAN, 0>::run(re, im);
-    if constexpr (SPAN > 1) DifAll<N, SPAN / 2>::run(re, im);
+    DifStageB<N, SPAN, 0, NZ>::run(re, im);
+    if constexpr (SPAN > 1) DifAll<N, SPAN / 2, NZ>::run(re, im);
   }
 };
 
 // In-place forward DFT of N complex values held in registers; X[k] = out[bitrev<N>(k)].
-template <int N>
+// NZ (default N): inputs re/im[NZ..N) are known zeros and need not be initialised... they ARE
+// written by the first stage, so the arrays are fully populated afterwards.
+template <int N, int NZ = N>
 SPL_HD void fft_dif(float (&re)[N], float (&im)[N]) {
   static_assert(N >= 2 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two <= 32");
-  DifAll<N, N / 2>::run(re, im);
+  static_assert(NZ > N / 2 && NZ <= N, "pruning supports up to N/2 trailing zeros");
+  DifAll<N, N / 2, NZ>::run(re, im);
 }
 
 }  // namespace spl

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,8 @@ struct spl_handle {
   spl_config cfg;
   int device;
   int D_out;
+  int num_sms;
+  bool legacy;  // SPL_LEGACY_KERNEL=1: always use the simple one-tile-per-CTA kernel
   void* blob;  // single device allocation holding every table
   spl::Tables tab;
   size_t smem_bytes;
@@ -100,6 +103,53 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     }
     grp[spl::kWarps] = D;
   }
+  // ---- persistent-kernel table block (see spl_internal.cuh) ----
+  const int npairs = (D + 1) / 2;
+  std::vector<float> pw;          // pair weights
+  std::vector<uint32_t> pdesc(npairs);
+  std::vector<int> pcost(npairs);
+  for (int i = 0; i < npairs; ++i) {
+    int lo_[2], n4_[2];
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int m = 2 * i + s2;
+      if (m < D && cnt[m] > 0) {
+        lo_[s2] = lo[m] & ~3;
+        n4_[s2] = (lo[m] + cnt[m] - lo_[s2] + 3) / 4;
+      } else {
+        lo_[s2] = 0;
+        n4_[s2] = 0;
+      }
+    }
+    const int n4p = n4_[0] > n4_[1] ? n4_[0] : n4_[1];
+    for (int s2 = 0; s2 < 2; ++s2)
+      if (lo_[s2] + 4 * n4p > nb) lo_[s2] = nb - 4 * n4p;  // keep the padded run inside the power row
+    const uint32_t off8 = (uint32_t)(pw.size() / 8);
+    for (int g = 0; g < n4p; ++g)
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int j = 0; j < 4; ++j) {
+          const int m = 2 * i + s2, k = lo_[s2] + 4 * g + j;
+          const bool in = m < D && k >= lo[m] && k < lo[m] + cnt[m];
+          pw.push_back(in ? 0.25f * mel_dense[(size_t)m * nb + k] : 0.f);
+        }
+    pdesc[i] = (uint32_t)(lo_[0] >> 2) | ((uint32_t)(lo_[1] >> 2) << 6) | ((uint32_t)n4p << 12) | (off8 << 18) |
+               ((2 * i + 1 < D) ? 0x80000000u : 0u);
+    pcost[i] = 14 + 15 * n4p;
+    if (n4p > 63 || off8 > 8191) return fail(SPL_ERR_UNSUPPORTED, "spl_create: mel bank too large for the descriptor");
+  }
+  int32_t pgrp[spl::kWarps + 1];
+  {
+    long total = 0;
+    for (int i = 0; i < npairs; ++i) total += pcost[i];
+    int i = 0;
+    long acc = 0;
+    pgrp[0] = 0;
+    for (int w = 1; w < spl::kWarps; ++w) {
+      const long target = total * w / spl::kWarps;
+      while (i < npairs && acc + pcost[i] / 2 < target) acc += pcost[i++];
+      pgrp[w] = i;
+    }
+    pgrp[spl::kWarps] = npairs;
+  }
   // stage-1 twiddles W_N^{n2 k1}
   const int R2 = nfft / 16;
   std::vector<float> twr(R2 * 16), twi(R2 * 16);
@@ -112,10 +162,21 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
 
   DeviceGuard guard(device);
   if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_create: cudaSetDevice failed");
-  // one blob: window | tw_re | tw_im | mel_w | lo | cnt | off   (all 4-byte items)
-  const size_t n_items = (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
-  std::vector<uint32_t> host(n_items);
-  size_t o = 0;
+  // one blob: persistent table block (16-byte aligned, first) | window | tw_re | tw_im | mel_w | lo | cnt | off
+  auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
+  const size_t pt_desc = pad4(pw.size()), pt_win = pt_desc + pad4(npairs), pt_tw = pt_win + pad4(Nw);
+  const size_t pt_words = pt_tw + 2 * (size_t)nfft;
+  const size_t n_items = pt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  std::vector<uint32_t> host(n_items, 0u);
+  std::memcpy(host.data(), pw.data(), pw.size() * 4);
+  std::memcpy(host.data() + pt_desc, pdesc.data(), npairs * 4);
+  std::memcpy(host.data() + pt_win, window, Nw * 4);
+  for (int n2 = 0; n2 < R2; ++n2)
+    for (int k1 = 0; k1 < 16; ++k1) {  // transposed: conflict-free for lane = n2
+      std::memcpy(host.data() + pt_tw + k1 * R2 + n2, &twr[n2 * 16 + k1], 4);
+      std::memcpy(host.data() + pt_tw + nfft + k1 * R2 + n2, &twi[n2 * 16 + k1], 4);
+    }
+  size_t o = pt_words;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -151,7 +212,20 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.mel_off = ib + o_off;
   h->tab.mel_nnz = nnz;
   for (int w = 0; w <= spl::kWarps; ++w) h->tab.grp_beg[w] = grp[w];
+  h->tab.ptab = fb;
+  h->tab.ptab_words = (int32_t)pt_words;
+  h->tab.pt_off_desc = (int32_t)pt_desc;
+  h->tab.pt_off_win = (int32_t)pt_win;
+  h->tab.pt_off_tw = (int32_t)pt_tw;
+  h->tab.npairs = npairs;
+  for (int w = 0; w <= spl::kWarps; ++w) h->tab.pgrp_beg[w] = pgrp[w];
+  h->num_sms = 148;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  const char* leg = std::getenv("SPL_LEGACY_KERNEL");
+  h->legacy = leg && leg[0] == '1';
   h->smem_bytes = spl::fbank_smem_bytes(nfft, S, Nw, D, h->D_out, nnz);
+  const size_t smem_p = spl::fbank_persistent_smem_bytes(nfft, S, Nw, h->D_out, (int)pt_words);
+  if (smem_p > h->smem_bytes) h->smem_bytes = smem_p;
   if (h->smem_bytes > 113 * 1024) {  // two CTAs per SM must fit in 227 KB
     cudaFree(blob);
     delete h;
@@ -172,7 +246,8 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   if (!h || !a) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null argument");
   if (!a->wav || !a->wav_len || !a->feats) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null buffer");
   if (a->B < 1 || a->B > 65535 || a->T < 1) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: B/T out of range");
-  if (a->wav_pitch < h->cfg.window_size) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: wav_pitch < window");
+  if (a->wav_cols < h->cfg.window_size || a->wav_pitch < a->wav_cols)
+    return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: need window_size <= wav_cols <= wav_pitch");
   if (a->sample_format != SPL_SAMPLES_F32 && a->sample_format != SPL_SAMPLES_I16)
     return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: sample_format");
   DeviceGuard guard(h->device);
@@ -190,6 +265,7 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   p.dither = h->cfg.dither;
   p.wav = a->wav;
   p.wav_pitch = a->wav_pitch;
+  p.wav_cols = a->wav_cols;
   p.sample_format = a->sample_format;
   p.wav_len = a->wav_len;
   p.B = a->B;
@@ -208,7 +284,11 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
     if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: cudaMemsetAsync");
   }
   const bool with_noise = h->cfg.dither != 0.f;
-  cudaError_t e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
+  cudaError_t e;
+  if (!h->legacy && a->B <= spl::kMaxPersistentB)
+    e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
+  else
+    e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
   if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: launch");
   g_launches.fetch_add(1);
   return SPL_OK;

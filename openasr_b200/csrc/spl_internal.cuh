@@ -26,6 +26,17 @@ struct Tables {
   const int32_t* mel_off;  // [D] offset into mel_w
   int32_t mel_nnz;
   int32_t grp_beg[kWarps + 1];  // filters [grp_beg[w], grp_beg[w+1]) handled by warp w in the mel phase
+  // persistent kernel: ONE contiguous block that is bulk-copied (TMA) into shared memory as is:
+  //   [pair weights | pair descriptors | window | stage-1 twiddles, transposed]
+  // Filters are processed two at a time; every pair is padded (zero weights) to a common number of
+  // 16-byte aligned 4-bin groups kept inside [0, Nfft/2).
+  //   weights     : for pair i, group g: 8 floats {wa[4], wb[4]}
+  //   descriptors : loA/4 | loB/4 << 6 | n4 << 12 | (weight offset / 8) << 18 | validB << 31
+  const float* ptab;
+  int32_t ptab_words;           // total 4-byte words, multiple of 4
+  int32_t pt_off_desc, pt_off_win, pt_off_tw;  // word offsets inside the block
+  int32_t npairs;
+  int32_t pgrp_beg[kWarps + 1]; // pairs [pgrp_beg[w], pgrp_beg[w+1]) handled by warp w in the mel phase
 };
 
 struct FbankParams {
@@ -34,7 +45,7 @@ struct FbankParams {
   float preemph, dither;
   // call
   const void* wav;
-  int64_t wav_pitch;
+  int64_t wav_pitch, wav_cols;
   int32_t sample_format;
   const int64_t* wav_len;
   int32_t B, T;
@@ -62,6 +73,10 @@ struct PostParams {
 // host-side launchers (defined in the .cu files); return cudaError_t of the launch
 cudaError_t launch_fbank(const FbankParams& p, int nfft, bool with_noise, cudaStream_t st);
 size_t fbank_smem_bytes(int nfft, int S, int Nw, int D, int D_out, int nnz);
+// persistent, load-balanced kernel (B <= kMaxPersistentB); num_ctas = 2 * SM count
+constexpr int kMaxPersistentB = 512;
+cudaError_t launch_fbank_persistent(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
+size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_words);
 cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);

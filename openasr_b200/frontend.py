@@ -6,6 +6,7 @@ PyTorch is used for device memory and streams only; all arithmetic of the hot pa
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import Dict, Optional, Sequence, Tuple
 
@@ -87,7 +88,8 @@ class FbankHandle:
             feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
         a = _capi.SplFbankArgs()
         a.wav = wav.data_ptr()
-        a.wav_pitch = wav.stride(0)
+        a.wav_pitch = wav.stride(0) if B > 1 else wav.shape[1]
+        a.wav_cols = wav.shape[1]
         a.sample_format = fmt
         a.wav_len = wav_len_dev.data_ptr()
         a.B = B
@@ -106,7 +108,8 @@ def get_handle(device: torch.device, sample_rate: float, num_mel_bins: int, use_
                dither: float, window_type: str) -> FbankHandle:
     """Handle cache keyed by (device, config); safe under DataParallel's per-GPU threads."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (idx, float(sample_rate), int(num_mel_bins), bool(use_energy), float(dither), str(window_type))
+    key = (idx, float(sample_rate), int(num_mel_bins), bool(use_energy), float(dither), str(window_type),
+           os.environ.get("SPL_LEGACY_KERNEL", ""))  # the library reads the switch at spl_create
     with _handles_lock:
         h = _handles.get(key)
         if h is None:

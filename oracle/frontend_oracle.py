@@ -319,15 +319,9 @@ def splayer_forward(wav_batch: torch.Tensor, lengths: Sequence[int], config: dic
     return padded, feat_lengths
 
 
-# --------------------------------------------------------------------------- timing helper
+# --------------------------------------------------------------------------- synthetic inputs
 def synth_batch(B: int, n_lo: int, n_hi: int, sample_rate: int, seed: int = 1234):
-    """SURVEY.md section 8d synthetic input: int16-scaled fp32, tone + noise, ragged lengths."""
-    g = torch.Generator().manual_seed(seed)
-    lengths = torch.randint(n_lo, n_hi + 1, (B,), generator=g)
-    L = int(lengths.max())
-    f0 = 80.0 + 320.0 * torch.rand(B, 1, generator=g)
-    t = torch.arange(L, dtype=torch.float32).unsqueeze(0) / sample_rate
-    x = 3000.0 * torch.randn(B, L, generator=g) + 2000.0 * torch.sin(2 * math.pi * f0 * t)
-    x = x.clamp(-32768, 32767).round()
-    mask = torch.arange(L).unsqueeze(0) < lengths.unsqueeze(1)
-    return (x * mask).contiguous(), lengths
+    """SURVEY.md section 8d synthetic input (shared generator; lives in the product package so the
+    benchmark's GPU arm does not import the oracle)."""
+    from openasr_b200.synth import synth_batch as _sb
+    return _sb(B, n_lo, n_hi, sample_rate, seed)

@@ -18,13 +18,24 @@ pytestmark = pytest.mark.gpu
 ATOL, RTOL = 1e-3, 1e-4
 
 
-def close(a, b):
+def close(a, b, b64=None, scale=None):
+    """|a - b| <= 1e-3 + 1e-4 |b| elementwise.  ``b64`` (the fp64 oracle) widens the bound by twice the
+    reference's OWN fp32 error on ill-conditioned elements (log of a mel bin ~1e5 below the frame
+    energy: the fp32 reference itself is off by up to 4e-3 there); at most 0.1 % of the
+    elements may need that.  ``scale`` multiplies the bound (features normalised by 1/std)."""
     a, b = a.detach().cpu().float(), b.detach().cpu().float()
     assert a.shape == b.shape, (a.shape, b.shape)
     d = (a - b).abs()
     assert torch.isfinite(a).all()
-    ok = d <= ATOL + RTOL * b.abs()
-    assert ok.all(), "max|d|=%g at %s" % (d.max().item(), np.unravel_index(int(d.argmax()), tuple(d.shape)))
+    tol = ATOL + RTOL * b.abs()
+    if scale is not None:
+        tol = tol * scale
+    if b64 is not None:
+        self_gap = (b.double() - b64.detach().cpu().double()).abs().float()
+        assert (d > tol).float().mean().item() <= 1e-3, "too many ill-conditioned elements"
+        tol = tol + 2.0 * self_gap
+    ok = d <= tol
+    assert ok.all(), "max|d|=%g at %s" % (d.max().item(), np.unravel_index(int((d - tol).argmax()), tuple(d.shape)))
     return d.max().item()
 
 
@@ -169,8 +180,9 @@ def test_synthetic_shapes_vs_oracle(sr, D, B, lo, hi):
     x, lens = fo.synth_batch(max(2, B // 4), lo, hi, sr, seed=1234)
     feats, flen = layer(x.cuda(), lens)
     ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
+    ref64, _ = fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)
     assert torch.equal(flen.cpu(), rlen)
-    close(feats, ref)
+    close(feats, ref, ref64)
 
 
 def test_cmvn_utterance_vs_fp64_oracle(wavs):
@@ -225,12 +237,20 @@ def test_full_training_forward_c2_like():
     torch.manual_seed(77)
     uni = torch.rand(8, 6)
     ref, rlen = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni)
+    ref64, _ = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni, dtype=torch.float64)
     assert torch.equal(flen.cpu(), rlen)
-    close(feats, ref)
+    # CMVN divides by the per-dimension std-dev, so the log-mel tolerance scales by 1/std
+    raw, _ = fo.splayer_forward(x, lens.tolist(), dict(conf, cmvn="none"), training=False)
+    istd = torch.stack([1.0 / raw[i, :m].std(0, unbiased=False) for i, m in enumerate(rlen.tolist())])
+    scale = istd.clamp_min(1.0)[:, None, :]
+    close(feats, ref, ref64, scale=scale)
+    for i, m in enumerate(rlen.tolist()):  # padding rows stay exactly zero (no mask reaches them here)
+        assert (feats[i, m:] == 0).all() and (ref[i, m:] == 0).all()
     # eval mode: no SpecAug
     layer.eval()
     e, _ = layer(x.cuda(), lens)
-    close(e, fo.splayer_forward(x, lens.tolist(), conf, training=False)[0])
+    close(e, fo.splayer_forward(x, lens.tolist(), conf, training=False)[0],
+          fo.splayer_forward(x, lens.tolist(), conf, training=False, dtype=torch.float64)[0], scale=scale)
 
 
 def test_short_time_mask_quirk():
@@ -261,3 +281,44 @@ def test_errors_and_api():
     wc = WavConv({"d_model": 8}).cuda()
     y, ly = wc(torch.randn(2, 3200).cuda(), torch.tensor([3200, 1600]).cuda())
     assert y.shape == (2, 20, 8) and ly.tolist() == [20, 10]
+
+
+# --------------------------------------------------------------------------------------------- scheduling edges
+def test_persistent_kernel_matches_simple_kernel(monkeypatch, wavs):
+    """The load-balanced persistent kernel (TMA staging, chunked frame ranges) against the simple
+    one-tile-per-CTA kernel on ragged batches, misaligned rows and storage offsets."""
+    x, lens = fo.synth_batch(9, 500, 70000, 16000, seed=4)
+    x = torch.cat([x, torch.zeros(9, 3)], dim=1)          # odd row pitch -> unaligned rows
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SPL_LEGACY_KERNEL", mode)
+        layer, conf = make_layer(use_energy=True)
+        layer.eval()
+        xc = x.cuda()
+        outs[mode] = (layer(xc, lens)[0], layer(xc[:, 1:], (lens - 1).clamp_min(400))[0])
+    for a, b in zip(outs["0"], outs["1"]):  # different rounding order only (fma forms): well inside the tolerance
+        assert (a - b).abs().max().item() < 2e-3 and (a - b).abs().mean().item() < 1e-5
+    ref, _ = fo.splayer_forward(x, lens.tolist(), conf)
+    close(outs["0"][0], ref, fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)[0])
+
+
+def test_many_short_utterances_and_large_batches():
+    """Chunks spanning many 1-3 frame utterances; B = 512 (persistent) and B = 600 (simple-kernel fallback)."""
+    for B in (512, 600):
+        g = torch.Generator().manual_seed(B)
+        lens = torch.randint(400, 900, (B,), generator=g)
+        x = (1000 * torch.randn(B, 900, generator=g)).round()
+        x = x * (torch.arange(900)[None, :] < lens[:, None])
+        layer, conf = make_layer(num_mel_bins=40, cmvn="utterance")
+        layer.eval()
+        feats, flen = layer(x.cuda(), lens)
+        sub = list(range(0, B, 37))
+        ref, rlen = fo.splayer_forward(x[sub], lens[sub].tolist(), conf)
+        assert torch.equal(flen.cpu()[sub], rlen)
+        got = feats.cpu()[sub][:, :ref.shape[1]]
+        # one-frame utterances have zero variance: CMVN floors the variance, compare the others
+        multi = [i for i, m in enumerate(rlen.tolist()) if m > 1]
+        raw, _ = fo.splayer_forward(x[sub], lens[sub].tolist(), dict(conf, cmvn="none"))
+        istd = torch.stack([1.0 / raw[i, :max(m, 2)].std(0, unbiased=False).clamp_min(1e-3) for i, m in enumerate(rlen.tolist())])
+        close(got[multi], ref[multi], scale=istd.clamp_min(1.0)[multi][:, None, :])
+        assert (feats.cpu()[sub][:, ref.shape[1]:] == 0).all()
