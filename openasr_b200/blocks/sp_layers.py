@@ -28,6 +28,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -77,6 +78,7 @@ class SPLayer(nn.Module):
         # global CMVN (mean, 1/std): non-persistent so state_dict() stays empty (Speech_Models.py:219-228)
         self.register_buffer("_gmean", None, persistent=False)
         self.register_buffer("_gistd", None, persistent=False)
+        self._stager = frontend.HostStager()
 
     # ------------------------------------------------------------------ helpers
     def _handle(self, device: torch.device) -> frontend.FbankHandle:
@@ -176,6 +178,48 @@ class SPLayer(nn.Module):
 
         frontend._require_cuda(wav_batch, "wav_batch")
         need_stats = self._cmvn == "utterance" or (aug and int(self.spec_aug_conf["time_mask_num"]) > 0)
+        if self._dither_rng == "host" and self._dither != 0.0 or self._specaug_rng != "host":
+            return self._forward_general(wav_batch, lengths, aug, need_stats)
+
+        # ---- fast path: one pinned upload (lengths + mask rectangles), two kernel launches ----
+        dev = wav_batch.device
+        h = self._handle(dev)
+        lens = self._host_lengths(lengths)
+        B = wav_batch.shape[0]
+        if len(lens) != B:
+            raise ValueError("lengths must have one entry per utterance")
+        width = wav_batch.shape[1]
+        for n in lens:
+            assert 2 <= h.win <= n, "choose a window size %d that is [2, %d]" % (h.win, n)  # kaldi_signal.py:154
+            if n > width:
+                raise ValueError("length %d exceeds the padded batch width %d" % (n, width))
+        lens_np = np.asarray(lens, dtype=np.int64)
+        frames_np = 1 + (lens_np - h.win) // h.shift
+        T = int(frames_np.max())
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self._dither != 0.0 else 0
+        arrays = [lens_np]
+        nf = nt = 0
+        if aug:
+            conf = self.spec_aug_conf
+            nf, nt = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
+            u = frontend.specaug_uniforms(B, nf, nt, None).numpy()
+            arrays.append(frontend.specaug_rectangles_np(u, frames_np, T, h.d_out, conf))
+        keep, ptrs = self._stager.upload(arrays, dev)
+        utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
+        feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)
+        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        h.fbank(wav_batch, ptrs[0], T, dither_seed=seed, utt_stats=utt_stats, out=feats, feat_len=feat_len)
+        if self._cmvn != "none" or aug:
+            if self._cmvn == "global" and self._gmean is None:
+                raise RuntimeError("cmvn='global' needs set_global_cmvn() (see openasr_b200.cmvn)")
+            frontend.post_inplace(feats, feat_len, cmvn_mode=self._cmvn, norm_vars=self._cmvn_norm_vars,
+                                  utt_stats=utt_stats, global_mean=self._gmean, global_istd=self._gistd,
+                                  mask_params=ptrs[1] if aug else None, n_freq=nf, n_time=nt)
+        del keep  # stream-ordered allocator: the block is only reused behind the launches above
+        return feats, feat_len
+
+    def _forward_general(self, wav_batch, lengths, aug, need_stats):
+        """Parity-mode / device-RNG variants (host dither stream upload, torch.rand on the GPU)."""
         feats, (feat_len, frames, utt_stats) = self._fbank_batch(wav_batch, lengths, need_stats)
         if self._cmvn != "none" or aug:
             rect, nf, nt = (None, 0, 0)

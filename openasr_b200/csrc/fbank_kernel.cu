@@ -289,19 +289,19 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_kernel(const FbankParams p)
   }
   if (p.utt_stats != nullptr || p.global_stats != nullptr) {
     if (tid < D_out) {
-      float s1 = 0.f, s2 = 0.f;
+      double s1 = 0.0, s2 = 0.0;  // fp64: sum x^2 - mean^2 must survive std << mean
       for (int r = 0; r < nvalid; ++r) {
-        const float v = out_tile[r * Dp + tid];
+        const double v = (double)out_tile[r * Dp + tid];
         s1 += v;
-        s2 = fmaf(v, v, s2);
+        s2 = fma(v, v, s2);
       }
       if (p.utt_stats) {
-        atomicAdd(p.utt_stats + ((size_t)b * 2 + 0) * D_out + tid, (double)s1);
-        atomicAdd(p.utt_stats + ((size_t)b * 2 + 1) * D_out + tid, (double)s2);
+        atomicAdd(p.utt_stats + ((size_t)b * 2 + 0) * D_out + tid, s1);
+        atomicAdd(p.utt_stats + ((size_t)b * 2 + 1) * D_out + tid, s2);
       }
       if (p.global_stats) {
-        atomicAdd(p.global_stats + tid, (double)s1);
-        atomicAdd(p.global_stats + D_out + tid, (double)s2);
+        atomicAdd(p.global_stats + tid, s1);
+        atomicAdd(p.global_stats + D_out + tid, s2);
       }
     }
     if (p.global_stats && tid == 0) atomicAdd(p.global_stats + 2 * D_out, (double)nvalid);

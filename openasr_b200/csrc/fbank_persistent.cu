@@ -14,9 +14,7 @@
 //     zero-padded rows of the radix-16 stage are pruned;
 //   * Philox4x32-7 with five 24-bit uniforms per call, MUFU lg2/sqrt/cos for the dither;
 //   * mel filters padded to groups of 4 bins: one broadcast LDS.128 of weights per 4 FMAs.
-#include <cuda/std/cstdint>
-
-#include "fbank_common.cuh"
+#include "fbank_frame.cuh"
 
 namespace spl {
 
@@ -55,163 +53,6 @@ __host__ __device__ inline PLayout make_playout(int nfft, int S, int Nw, int D_o
 
 size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_words) {
   return sizeof(float) * (size_t)make_playout(nfft, S, Nw, D_out, ptab_words).total;
-}
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint32_t addr = smem_u32(bar);
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// Philox4x32-7 (Salmon et al. 2011: 7 rounds is the Crush-resistant minimum; 10 is the default)
-__device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return ctr;
-}
-
-// dither * g(u) for a 24-bit uniform v = u * 2^24 (kaldi_signal.py:176-177):
-//   x = max(eps, u) (eps = 2^-23 <=> v >= 2),  g = sqrt(-2 ln x) * cos(2 pi x).
-// d2 = dither^2 folded under the square root.
-__device__ __forceinline__ float dither_term(uint32_t v24, float d2) {
-  const float v = (float)max(v24, 2u);
-  // -2 ln(v 2^-24) = (24 - lg2 v) * 2 ln 2
-  const float a = fmaf(__log2f(v), -1.3862943611198906f * d2, 33.27106466687737f * d2);
-  return fast_sqrt(a) * __cosf(v * 3.7450703370559213e-07f);  // 2 pi 2^-24
-}
-
-// ---------------------------------------------------------------------------------------------
-// Compile-time frame geometry: lane n2 of the stage-1 layout holds samples j = R2*n1 + n2.
-template <int NFFT, int NW>
-struct FG {
-  static constexpr int R2 = NFFT / 16;
-  static constexpr bool kStatic = NW > 0;
-  static constexpr int NROW = kStatic ? (NW + R2 - 1) / R2 : 16;  // rows that can be non-zero
-  static constexpr int FULL = kStatic ? NW / R2 : 0;              // rows valid for every lane
-  static constexpr int REM = kStatic ? NW - FULL * R2 : 0;        // lanes valid in row FULL
-  static_assert(!kStatic || NROW > 8, "window must exceed half the padded size");
-};
-
-template <int NFFT, int NW>
-__device__ __forceinline__ bool row_valid(int n1, int n2, int Nw) {
-  using F = FG<NFFT, NW>;
-  if constexpr (F::kStatic) return n1 < F::FULL || n2 < F::REM;
-  return F::R2 * n1 + n2 < Nw;
-}
-
-// One frame in the stage-1 register layout.  kaldi_signal.py:174-199:
-// dither -> DC removal -> raw log-energy -> pre-emphasis -> window.
-//   z_j = w_j * ((x_j - mu) - c (x_{j-1} - mu)) = w_j * (x_j - c x_{j-1} - (1-c) mu),  x_{-1} := x_0
-template <int NFFT, int NW, bool NOISE>
-__device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& p, const float* fr /*frame's first sample*/,
-                                             const float* win, float* energy_slot, int n2, int b, int t, bool valid) {
-  using G = Geo<NFFT>;
-  using F = FG<NFFT, NW>;
-  const int Nw = F::kStatic ? NW : p.Nw;
-  float x[F::NROW];
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) x[n1] = row_valid<NFFT, NW>(n1, n2, Nw) ? fr[G::R2 * n1 + n2] : 0.f;
-
-  if constexpr (NOISE) {
-    if (valid) {
-      if (p.noise != nullptr) {  // parity mode: host-drawn rand_gauss, [B, T, Nw]
-        const float* nz = p.noise + ((size_t)b * p.T + t) * Nw;
-#pragma unroll
-        for (int n1 = 0; n1 < F::NROW; ++n1)
-          if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = fmaf(__ldg(nz + G::R2 * n1 + n2), p.dither, x[n1]);
-      } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call)
-        const float d2 = p.dither * p.dither;
-        const float sgn = p.dither < 0.f ? -1.f : 1.f;
-#pragma unroll
-        for (int c5 = 0; c5 * 5 < F::NROW; ++c5) {
-          const uint4 r = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)t, (uint32_t)b, 0x5eedu),
-                                       p.seed_lo, p.seed_hi);
-          const uint32_t v[5] = {r.x >> 8, r.y >> 8, r.z >> 8, r.w >> 8,
-                                 ((r.x & 0xffu) << 16) | ((r.y & 0xffu) << 8) | (r.z & 0xffu)};
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const int n1 = 5 * c5 + i;
-            if (n1 < F::NROW) {
-              const float g = dither_term(v[i], d2) * sgn;
-              if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] += g;
-            }
-          }
-        }
-      }
-    }
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) sum += x[n1];
-  float mean = 0.f;
-  if (p.remove_dc) mean = group_sum(sum, G::R2) * (1.0f / (float)Nw);
-  if (p.use_energy) {
-    float e = 0.f;
-#pragma unroll
-    for (int n1 = 0; n1 < F::NROW; ++n1) {
-      const float d = row_valid<NFFT, NW>(n1, n2, Nw) ? x[n1] - mean : 0.f;
-      e = fmaf(d, d, e);
-    }
-    e = group_sum(e, G::R2);
-    if (n2 == 0) *energy_slot = __logf(fmaxf(e, kEps));
-  }
-  const float c = p.preemph;
-  const float mu = (1.0f - c) * mean;
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) {
-    float prev;
-    if constexpr (NOISE) {  // previous sample of the noisy frame lives in the neighbouring lane
-      const float up = __shfl_up_sync(0xffffffffu, x[n1], 1, G::R2);
-      float wrap = x[0];  // j == 0: replicate padding (kaldi_signal.py:192-193)
-      if (n1 > 0) wrap = __shfl_sync(0xffffffffu, x[n1 - 1], G::R2 - 1, G::R2);
-      prev = (n2 == 0) ? wrap : up;
-    } else {
-      const int j = G::R2 * n1 + n2;
-      prev = (n1 == 0 && n2 == 0) ? x[0] : fr[(row_valid<NFFT, NW>(n1, n2, Nw) ? j : 1) - 1];
-    }
-    const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
-    const float wj = rv ? win[G::R2 * n1 + n2] : 0.f;
-    z[n1] = (fmaf(-c, prev, x[n1]) - mu) * wj;
-  }
-#pragma unroll
-  for (int n1 = F::NROW; n1 < 16; ++n1) z[n1] = 0.f;
-  (void)valid;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,19 +383,19 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_persistent_kernel(const Fba
       }
       if (p.utt_stats != nullptr || p.global_stats != nullptr) {
         if (tid < D_out) {
-          float s1 = 0.f, s2 = 0.f;
+          double s1 = 0.0, s2 = 0.0;  // fp64: sum x^2 - mean^2 must survive std << mean
           for (int r = 0; r < nf; ++r) {
-            const float v = warp_base[(r >> 2) * RW + OUT_OFF + (r & 3) * OP + tid];
+            const double v = (double)warp_base[(r >> 2) * RW + OUT_OFF + (r & 3) * OP + tid];
             s1 += v;
-            s2 = fmaf(v, v, s2);
+            s2 = fma(v, v, s2);
           }
           if (p.utt_stats) {
-            atomicAdd(p.utt_stats + ((size_t)c.b * 2 + 0) * D_out + tid, (double)s1);
-            atomicAdd(p.utt_stats + ((size_t)c.b * 2 + 1) * D_out + tid, (double)s2);
+            atomicAdd(p.utt_stats + ((size_t)c.b * 2 + 0) * D_out + tid, s1);
+            atomicAdd(p.utt_stats + ((size_t)c.b * 2 + 1) * D_out + tid, s2);
           }
           if (p.global_stats) {
-            atomicAdd(p.global_stats + tid, (double)s1);
-            atomicAdd(p.global_stats + D_out + tid, (double)s2);
+            atomicAdd(p.global_stats + tid, s1);
+            atomicAdd(p.global_stats + D_out + tid, s2);
           }
         }
         if (p.global_stats && tid == 0) atomicAdd(p.global_stats + 2 * D_out, (double)nf);

@@ -1,0 +1,503 @@
+// Kernel A (warp-pipelined): fused frame -> (dither) -> DC removal -> pre-emphasis -> window ->
+// real FFT -> power -> sparse mel -> log, one CTA of 16 *independent* warps per SM.
+//
+// Replaces src/third_party/kaldi_signal.py:163-211 + :510-552 and the pad/stack loop of
+// src/blocks/sp_layers.py:81-91.  Same arithmetic as fbank_kernel.cu / fbank_persistent.cu;
+// what changes is the execution structure, driven by the ncu profiles under profiles/:
+//   * the unit of work is a GROUP of <= 4 consecutive frames of one utterance, processed end to
+//     end by ONE warp: TMA bulk copy of the group's samples -> two packed complex FFTs ->
+//     power rows -> mel (lane = frame x filter slice) -> log -> coalesced store.  Inside the main
+//     loop there is no __syncthreads: warps never wait for each other, only for their own TMA;
+//   * every CTA owns an equal, contiguous share of the batch's group list and its warps pull
+//     groups from a shared-memory counter, so the load balance is at 4-frame granularity;
+//   * the sample buffer aliases the second pair's exchange planes (dead until the stage-1 output
+//     of that pair is written), so the next group's samples land behind FFT stage 2 / mel / store;
+//   * per-utterance CMVN sums are kept in registers, merged per CTA in shared memory and flushed
+//     with one fp64 atomic per (utterance, column) per CTA.
+#include "fbank_frame.cuh"
+
+namespace spl {
+
+constexpr int kWWarps = 8;   // two such CTAs per SM: 16 resident warps (register-file bound at 128 regs)
+constexpr int kWThreads = kWWarps * 32;
+constexpr int kStatUtts = 4;  // utterances a CTA can merge in shared memory (more: direct global atomics)
+
+struct WLayout {
+  int pair;      // floats of one pair's exchange area (re plane + im plane)
+  int p1;        // offset of pair 1's area (== 16 mod 32 away from pair 0: conflict-free stage-2 reads)
+  int out_off;   // output rows (4 x op)
+  int op;        // output-row pitch
+  int en_off;    // 4 energy slots
+  int st_off;    // this warp's running column sums of the current utterance: [2][op]
+  int rw;        // region stride (multiple of 4)
+  int off_tab, off_gpre, off_fpre, off_stat, off_ctl, off_bar, off_warp, total;
+};
+
+__host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words) {
+  WLayout L;
+  const int pl = nfft == 512 ? Geo<512>::PL : Geo<256>::PL;
+  L.pair = 2 * pl;
+  L.p1 = L.pair + 16;
+  L.op = (D_out + 3) & ~3;
+  L.out_off = L.p1 + L.pair;
+  L.en_off = L.out_off + 4 * L.op;
+  L.st_off = L.en_off + 4;
+  L.st_off = (L.st_off + 1) & ~1;  // fp64 rows, 8-byte aligned
+  L.rw = (L.st_off + 4 * L.op + 3) & ~3;
+  L.off_tab = 0;
+  L.off_gpre = wtab_words;
+  L.off_fpre = L.off_gpre + kMaxPersistentB + 1;
+  L.off_stat = (L.off_fpre + kMaxPersistentB + 1 + 3) & ~3;
+  L.off_ctl = L.off_stat + kStatUtts * 4 * L.op;  // fp64 [kStatUtts][2][op]
+  L.off_bar = (L.off_ctl + 8 + 1) & ~1;
+  L.off_warp = (L.off_bar + 2 * (kWWarps + 1) + 31) & ~31;
+  L.total = L.off_warp + kWWarps * L.rw;
+  (void)S;
+  (void)Nw;
+  return L;
+}
+
+size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words) {
+  return sizeof(float) * (size_t)make_wlayout(nfft, S, Nw, D_out, wtab_words).total;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NFFT, int NW, bool NOISE>
+__global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankParams p) {
+  using G = Geo<NFFT>;
+  using F = FG<NFFT, NW>;
+  extern __shared__ __align__(128) float smem[];
+  const int S = p.S, Nw = F::kStatic ? NW : p.Nw, D_out = p.D_out;
+  const WLayout L = make_wlayout(NFFT, S, Nw, D_out, p.tab.wtab_words);
+  static_assert(2 * G::PL >= 4 * G::PP, "power rows must fit in pair 0's exchange area");
+  float* tab = smem + L.off_tab;
+  const float4* melw = reinterpret_cast<const float4*>(tab);
+  const uint32_t* pdesc = reinterpret_cast<const uint32_t*>(tab + p.tab.wt_off_desc);
+  const uint32_t* jinfo = reinterpret_cast<const uint32_t*>(tab + p.tab.wt_off_jinfo);
+  const float* win = tab + p.tab.wt_off_win;
+  const float* tws = tab + p.tab.wt_off_tw;
+  int* gpre = reinterpret_cast<int*>(smem + L.off_gpre);  // gpre[b] = groups of utterances < b
+  int* fpre = reinterpret_cast<int*>(smem + L.off_fpre);  // fpre[b] = frames of utterances < b
+  double* cstat = reinterpret_cast<double*>(smem + L.off_stat);  // [kStatUtts][2][op]
+  int* ctl = reinterpret_cast<int*>(smem + L.off_ctl);    // [0] next group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [0] tables, [1 + w] samples of warp w
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int B = p.B, T = p.T, OP = L.op;
+  float* wr = smem + L.off_warp + w * L.rw;  // this warp's region
+  float* e0 = wr;                            // pair 0 exchange: re plane, im plane at + PL ; power rows alias it
+  float* e1 = wr + L.p1;                     // pair 1 exchange ; the sample buffer aliases it
+  float* samp = e1;
+  float* orows = wr + L.out_off;
+  float* energy = wr + L.en_off;
+  double* wstat = reinterpret_cast<double*>(wr + L.st_off);  // fp64: sum x^2 - mean^2 must survive std << mean
+  uint64_t* mybar = bars + 1 + w;
+
+  // ---- 0. tables (one TMA bulk copy), group prefix (warp 0), barriers -----------------------------
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    for (int i = 0; i < kWWarps; ++i) mbar_init(bars + 1 + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bars, (uint32_t)p.tab.wtab_words * 4u);
+    bulk_g2s(tab, p.tab.wtab, (uint32_t)p.tab.wtab_words * 4u, bars);
+  }
+  for (int i = tid; i < kStatUtts * 2 * OP; i += kWThreads) cstat[i] = 0.0;
+  if (w == 0) {
+    int carry = 0, fcarry = 0;
+    for (int base = 0; base < B; base += 32) {
+      const int bb = base + lane;
+      int m = 0;
+      if (bb < B) {
+        const long long n = p.wav_len[bb];
+        m = n >= Nw ? (int)(1 + (n - Nw) / S) : 0;  // kaldi_signal.py:90
+        m = m > T ? T : m;
+        if (blockIdx.x == 0 && p.feat_len) p.feat_len[bb] = m;
+      }
+      const int gcount = (m + 3) >> 2;
+      int incl = gcount, finc = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        const int u = __shfl_up_sync(0xffffffffu, finc, o);
+        if (lane >= o) {
+          incl += v;
+          finc += u;
+        }
+      }
+      if (bb < B) {
+        gpre[bb] = carry + incl - gcount;
+        fpre[bb] = fcarry + finc - m;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      fcarry += __shfl_sync(0xffffffffu, finc, 31);
+    }
+    if (lane == 0) {
+      gpre[B] = carry;
+      fpre[B] = fcarry;
+    }
+  }
+  for (int i = lane; i < 2 * OP; i += 32) wstat[i] = 0.0;
+  __syncthreads();
+  if (tid == 0) {  // this CTA's contiguous share of the group list (64-bit division once, not per thread)
+    const long long NG = gpre[B];
+    const int g0 = (int)(NG * blockIdx.x / gridDim.x), g1 = (int)(NG * (blockIdx.x + 1) / gridDim.x);
+    int lo = 0, hi = B - 1;  // utterance of the first group
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (gpre[mid] <= g0) lo = mid; else hi = mid - 1;
+    }
+    ctl[0] = g0;  // next group to hand out
+    ctl[1] = g1;
+    ctl[2] = lo;
+    // share of the B*T - frames zero-padding rows
+    const long long total_pad = (long long)B * T - fpre[B];
+    ctl[3] = (int)(total_pad * blockIdx.x / gridDim.x);
+    ctl[4] = (int)(total_pad * (blockIdx.x + 1) / gridDim.x);
+  }
+  __syncthreads();
+  const int g1 = ctl[1], b_first = ctl[2];
+
+  // ---- 0b. zero padding rows: an equal share of the padded rows per CTA (sp_layers.py:88) -------
+  {
+    int q = ctl[3];
+    const int q1 = ctl[4];
+    if (q < q1) {
+      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+      }
+      int b = lo;
+      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
+      while (q < q1) {
+        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
+        const int m_b = fpre[b + 1] - fpre[b];
+        const int ofs = q - (b * T - fpre[b]);
+        int nrows = (T - m_b) - ofs;
+        nrows = nrows > q1 - q ? q1 - q : nrows;
+        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
+        if (vec) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const int n4 = nrows * (D_out >> 2);
+          for (int i = tid; i < n4; i += kWThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int i = tid; i < nrows * D_out; i += kWThreads) dst[i] = 0.f;
+        }
+        q += nrows;
+      }
+    }
+  }
+
+  // ---- per-warp helpers ---------------------------------------------------------------------------
+  const char* wav_lo = static_cast<const char*>(p.wav);
+  const size_t esz = p.sample_format == SPL_SAMPLES_F32 ? 4 : 2;
+  const char* wav_hi = wav_lo + ((size_t)(B - 1) * p.wav_pitch + (size_t)p.wav_cols) * esz;
+  int b_hint = b_first;
+  auto fetch_group = [&]() {  // warp-uniform: next group id of this CTA (or >= g1)
+    int g = 0;
+    if (lane == 0) g = atomicAdd(ctl, 1);
+    return __shfl_sync(0xffffffffu, g, 0);
+  };
+  struct Grp {
+    int b, t0, n, head;
+    bool bulk;
+  };
+  // Locate group g and start staging its samples into `samp`.
+  auto stage_group = [&](int g, Grp& q) {
+    int b = b_hint;
+    while (gpre[b + 1] <= g) ++b;
+    b_hint = b;
+    q.b = b;
+    q.t0 = 4 * (g - gpre[b]);
+    const int left = (fpre[b + 1] - fpre[b]) - q.t0;
+    q.n = left < 4 ? left : 4;
+    const int need = (q.n - 1) * S + Nw;
+    q.bulk = false;
+    q.head = 0;
+    if (p.sample_format == SPL_SAMPLES_F32) {
+      const char* src = wav_lo + ((size_t)b * p.wav_pitch + (size_t)q.t0 * S) * 4;
+      const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
+      const int head = (int)((src - a0) >> 2);
+      const uint32_t bytes = (uint32_t)(((head + need) * 4 + 15) & ~15);
+      if (a0 >= wav_lo && a0 + bytes <= wav_hi) {
+        q.bulk = true;
+        q.head = head;
+        if (lane == 0) {
+          fence_proxy_async();  // earlier generic-proxy accesses of this area precede the async writes
+          mbar_expect_tx(mybar, bytes);
+          bulk_g2s(samp, a0, bytes, mybar);
+        }
+      }
+    }
+  };
+
+  mbar_wait(bars, 0);  // tables have landed
+
+  // per-utterance column sums (CMVN / SpecAug time means): running sums of this warp's current
+  // utterance live in its own shared-memory rows and are merged into the CTA table on a change
+  int stat_b = -1, stat_rows = 0;
+  const bool want_stats = p.utt_stats != nullptr || p.global_stats != nullptr;
+  auto flush_stats = [&]() {
+    if (stat_b < 0) return;
+    const int slot = stat_b - b_first;
+    for (int c = lane; c < D_out; c += 32) {
+      const double v1 = wstat[c], v2 = wstat[OP + c];
+      wstat[c] = 0.0;
+      wstat[OP + c] = 0.0;
+      if (slot < kStatUtts) {
+        atomicAdd(cstat + (slot * 2 + 0) * OP + c, v1);
+        atomicAdd(cstat + (slot * 2 + 1) * OP + c, v2);
+      } else {
+        if (p.utt_stats) {
+          atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 0) * D_out + c, v1);
+          atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 1) * D_out + c, v2);
+        }
+        if (p.global_stats) {
+          atomicAdd(p.global_stats + c, v1);
+          atomicAdd(p.global_stats + D_out + c, v2);
+        }
+      }
+    }
+    if (p.global_stats && lane == 0) atomicAdd(p.global_stats + 2 * D_out, (double)stat_rows);
+    stat_rows = 0;
+  };
+
+  // ---- main loop: one group (<= 4 frames of one utterance) per iteration, no block-wide barriers ----
+  uint32_t parity = 0;
+  Grp cur, nxt;
+  int g_cur = fetch_group();
+  if (g_cur < g1) stage_group(g_cur, cur);
+  while (g_cur < g1) {
+    const int g_nxt = fetch_group();
+    const int n = cur.n;
+    const int need = (n - 1) * S + Nw;
+    if (cur.bulk) {
+      mbar_wait(mybar, parity);
+      parity ^= 1;
+    } else {  // scalar staging (int16 ingest, unaligned or boundary windows)
+      const size_t gofs = (size_t)cur.b * p.wav_pitch + (size_t)cur.t0 * S;
+      if (p.sample_format == SPL_SAMPLES_F32) {
+        const float* src = static_cast<const float*>(p.wav) + gofs;
+        for (int i = lane; i < need; i += 32) samp[i] = __ldg(src + i);
+      } else {
+        const int16_t* src = static_cast<const int16_t*>(p.wav) + gofs;
+        for (int i = lane; i < need; i += 32) samp[i] = (float)__ldg(src + i);
+      }
+      __syncwarp();
+    }
+    const float* sbase = samp + cur.head;
+    if (n < 4) {  // invalid frames must read finite data: zero everything past the valid span
+      for (int i = need + lane; i < 3 * S + Nw; i += 32) samp[cur.head + i] = 0.f;
+      __syncwarp();
+    }
+
+    // ---- stage 1: radix-16 over n1 (lane = n2), twiddle, transpose through the exchange planes ----
+    if constexpr (NFFT == 512) {
+      const int n2 = lane;
+      float twr[16], twi[16];
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        twr[k1] = tws[k1 * G::R2 + n2];
+        twi[k1] = tws[NFFT + k1 * G::R2 + n2];
+      }
+      float re[16], im[16], re1[16], im1[16];
+      load_frame_p<NFFT, NW, NOISE>(re, p, sbase, win, energy + 0, n2, cur.b, cur.t0, true);
+      load_frame_p<NFFT, NW, NOISE>(im, p, sbase + S, win, energy + 1, n2, cur.b, cur.t0 + 1, n > 1);
+      fft_dif<16, F::NROW>(re, im);
+      {
+        float* er = e0 + n2 * G::EP;
+        float* ei = er + G::PL;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+          const float vr = re[bitrev<16>(k1)], vi = im[bitrev<16>(k1)];
+          er[k1] = vr * twr[k1] + vi * twi[k1];  // * (c - i s)
+          ei[k1] = vi * twr[k1] - vr * twi[k1];
+        }
+      }
+      load_frame_p<NFFT, NW, NOISE>(re1, p, sbase + 2 * S, win, energy + 2, n2, cur.b, cur.t0 + 2, n > 2);
+      load_frame_p<NFFT, NW, NOISE>(im1, p, sbase + 3 * S, win, energy + 3, n2, cur.b, cur.t0 + 3, n > 3);
+      __syncwarp();  // every lane has its samples in registers: pair 1's planes may overwrite the buffer
+      fft_dif<16, F::NROW>(re1, im1);
+      {
+        float* er = e1 + n2 * G::EP;
+        float* ei = er + G::PL;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+          const float vr = re1[bitrev<16>(k1)], vi = im1[bitrev<16>(k1)];
+          er[k1] = vr * twr[k1] + vi * twi[k1];
+          ei[k1] = vi * twr[k1] - vr * twi[k1];
+        }
+      }
+    } else {
+      const int pr = lane >> 4, n2 = lane & 15;
+      const int fa = 2 * pr;
+      float re[16], im[16];
+      load_frame_p<NFFT, NW, NOISE>(re, p, sbase + fa * S, win, energy + fa, n2, cur.b, cur.t0 + fa, fa < n);
+      load_frame_p<NFFT, NW, NOISE>(im, p, sbase + (fa + 1) * S, win, energy + fa + 1, n2, cur.b, cur.t0 + fa + 1,
+                                    fa + 1 < n);
+      __syncwarp();  // samples are in registers; pair 1's planes alias the buffer
+      fft_dif<16, F::NROW>(re, im);
+      float* er = (pr ? e1 : e0) + n2 * G::EP;
+      float* ei = er + G::PL;
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float cs = tws[k1 * G::R2 + n2], sn = tws[NFFT + k1 * G::R2 + n2];
+        const float vr = re[bitrev<16>(k1)], vi = im[bitrev<16>(k1)];
+        er[k1] = vr * cs + vi * sn;
+        ei[k1] = vi * cs - vr * sn;
+      }
+    }
+    __syncwarp();
+
+    // ---- stage 2: lane = (pair, k1), registers = n2 ----
+    const int pr = lane >> 4, k1 = lane & 15;
+    float xr[G::R2], xi[G::R2];
+    {
+      const float* er = (pr ? e1 : e0) + k1;
+      const float* ei = er + G::PL;
+#pragma unroll
+      for (int n2 = 0; n2 < G::R2; ++n2) {
+        xr[n2] = er[n2 * G::EP];
+        xi[n2] = ei[n2 * G::EP];
+      }
+    }
+    __syncwarp();  // exchange planes dead: pair 0's area becomes the power rows, pair 1's the next samples
+    if (g_nxt < g1) stage_group(g_nxt, nxt);
+    fft_dif<G::R2>(xr, xi);
+
+    // Hermitian partner + power: Z[k1 + 16 k2] sits at register bitrev(k2)
+    {
+      const int partner = (lane & 16) | ((16 - k1) & 15);
+      float* pa = e0 + (2 * pr) * G::PP + k1;
+      float* pb = pa + G::PP;
+#pragma unroll
+      for (int k2 = 0; k2 < G::H; ++k2) {
+        const float zr = xr[bitrev<G::R2>(k2)], zi = xi[bitrev<G::R2>(k2)];
+        float qr = __shfl_sync(0xffffffffu, xr[bitrev<G::R2>(G::R2 - 1 - k2)], partner);
+        float qi = __shfl_sync(0xffffffffu, xi[bitrev<G::R2>(G::R2 - 1 - k2)], partner);
+        if (k1 == 0) {
+          qr = xr[bitrev<G::R2>((G::R2 - k2) & (G::R2 - 1))];
+          qi = xi[bitrev<G::R2>((G::R2 - k2) & (G::R2 - 1))];
+        }
+        const float ar = zr + qr, ai = zi - qi;
+        const float br = zi + qi, bi = qr - zr;
+        pa[16 * k2] = ar * ar + ai * ai;  // 4 |X_A|^2 (the 1/4 is folded into the mel weights)
+        pb[16 * k2] = br * br + bi * bi;
+      }
+    }
+    __syncwarp();
+
+    // ---- mel: lane = (frame f, slice s); iteration j handles filter pairs 8 j + s ----
+    {
+      const int f = lane & 3, sl = lane >> 2;
+      const float4* prow4 = reinterpret_cast<const float4*>(e0 + f * G::PP);
+      float* orow = orows + f * OP + (p.use_energy ? 1 : 0);
+      for (int j = 0; j < p.tab.nj; ++j) {
+        const uint32_t ji = jinfo[j];
+        const int n4 = ji & 255u;
+        const float4* wv = melw + (size_t)(ji >> 8) * 16 + sl;
+        const uint32_t dsc = pdesc[8 * j + sl];
+        const float4* pa4 = prow4 + (dsc & 63u);
+        const float4* pb4 = prow4 + ((dsc >> 6) & 63u);
+        float accA = 0.f, accB = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < n4; ++g) {
+          const float4 pa = pa4[g], pb = pb4[g];
+          const float4 wa = wv[16 * g], wb = wv[16 * g + 8];
+          accA = fmaf(pa.x, wa.x, accA);
+          accB = fmaf(pb.x, wb.x, accB);
+          accA = fmaf(pa.y, wa.y, accA);
+          accB = fmaf(pb.y, wb.y, accB);
+          accA = fmaf(pa.z, wa.z, accA);
+          accB = fmaf(pb.z, wb.z, accB);
+          accA = fmaf(pa.w, wa.w, accA);
+          accB = fmaf(pb.w, wb.w, accB);
+        }
+        const int m0 = 2 * (8 * j + sl);
+        if (dsc & 0x40000000u) orow[m0] = __logf(fmaxf(accA, kEps));  // kaldi_signal.py:540
+        if (dsc & 0x80000000u) orow[m0 + 1] = __logf(fmaxf(accB, kEps));
+      }
+      if (p.use_energy && lane < 4) orows[lane * OP] = energy[lane];
+    }
+    __syncwarp();
+
+    // ---- store the group's rows (contiguous in global memory) + column sums ----
+    {
+      float* out_g = p.feats + ((size_t)cur.b * T + cur.t0) * D_out;
+      if ((D_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0)) {
+        const int q = D_out >> 2;  // OP == D_out here: the rows are contiguous in shared memory too
+        const float4* src = reinterpret_cast<const float4*>(orows);
+        float4* dst = reinterpret_cast<float4*>(out_g);
+        for (int i = lane; i < n * q; i += 32) dst[i] = src[i];
+      } else {
+        for (int r = 0; r < n; ++r)
+          for (int c = lane; c < D_out; c += 32) out_g[(size_t)r * D_out + c] = orows[r * OP + c];
+      }
+      if (want_stats) {
+        if (cur.b != stat_b) {
+          flush_stats();
+          stat_b = cur.b;
+        }
+        stat_rows += n;
+        for (int c = lane; c < D_out; c += 32) {
+          double a1 = wstat[c], a2 = wstat[OP + c];
+          for (int r = 0; r < n; ++r) {
+            const double v = (double)orows[r * OP + c];
+            a1 += v;
+            a2 = fma(v, v, a2);
+          }
+          wstat[c] = a1;
+          wstat[OP + c] = a2;
+        }
+      }
+    }
+    __syncwarp();  // output rows / power rows are rewritten by the next iteration
+    g_cur = g_nxt;
+    cur = nxt;
+  }
+
+  // ---- epilogue: merge the CTA's column sums, one fp64 atomic per (utterance, column) ----
+  if (want_stats) {
+    flush_stats();
+    __syncthreads();
+    for (int sw = 0; sw < 2 * kStatUtts; ++sw) {
+      const int slot = sw >> 1, which = sw & 1, b = b_first + slot;
+      if (b >= B) break;
+      for (int c = tid; c < D_out; c += kWThreads) {
+        const double v = cstat[sw * OP + c];
+        if (v != 0.0) {
+          if (p.utt_stats) atomicAdd(p.utt_stats + ((size_t)b * 2 + which) * D_out + c, v);
+          if (p.global_stats) atomicAdd(p.global_stats + which * D_out + c, v);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NFFT, int NW, bool NOISE>
+static cudaError_t launch_w(const FbankParams& p, int num_ctas, cudaStream_t st) {
+  const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out, p.tab.wtab_words);
+  static thread_local size_t configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || configured[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(fbank_warp_kernel<NFFT, NW, NOISE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev < 16) configured[dev] = smem;
+  }
+  fbank_warp_kernel<NFFT, NW, NOISE><<<num_ctas, kWThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st) {
+  if (nfft == 512) {
+    if (p.Nw == 400) return with_noise ? launch_w<512, 400, true>(p, num_ctas, st) : launch_w<512, 400, false>(p, num_ctas, st);
+    return with_noise ? launch_w<512, 0, true>(p, num_ctas, st) : launch_w<512, 0, false>(p, num_ctas, st);
+  }
+  if (p.Nw == 200) return with_noise ? launch_w<256, 200, true>(p, num_ctas, st) : launch_w<256, 200, false>(p, num_ctas, st);
+  return with_noise ? launch_w<256, 0, true>(p, num_ctas, st) : launch_w<256, 0, false>(p, num_ctas, st);
+}
+
+}  // namespace spl

@@ -45,7 +45,8 @@ struct spl_handle {
   int device;
   int D_out;
   int num_sms;
-  bool legacy;  // SPL_LEGACY_KERNEL=1: always use the simple one-tile-per-CTA kernel
+  int kernel;  // 0 warp-pipelined (default), 1 simple one-tile-per-CTA (SPL_LEGACY_KERNEL=1), 2 persistent CTA tiles (=2)
+  size_t smem_warp;
   void* blob;  // single device allocation holding every table
   spl::Tables tab;
   size_t smem_bytes;
@@ -150,6 +151,45 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     }
     pgrp[spl::kWarps] = npairs;
   }
+  // ---- warp-pipelined kernel table block (see spl_internal.cuh) ----
+  const int nj = (npairs + 7) / 8;
+  std::vector<float> ww;
+  std::vector<uint32_t> wdesc(nj * 8, 0u), jinfo(nj, 0u);
+  {
+    int goff = 0;
+    for (int j = 0; j < nj; ++j) {
+      int lo_[8][2], n4j = 0;
+      for (int s2 = 0; s2 < 8; ++s2)
+        for (int hh = 0; hh < 2; ++hh) {
+          const int m = 2 * (8 * j + s2) + hh;
+          lo_[s2][hh] = 0;
+          if (m < D && cnt[m] > 0) {
+            lo_[s2][hh] = lo[m] & ~3;
+            const int n4m = (lo[m] + cnt[m] - lo_[s2][hh] + 3) / 4;
+            n4j = n4m > n4j ? n4m : n4j;
+          }
+        }
+      for (int s2 = 0; s2 < 8; ++s2)
+        for (int hh = 0; hh < 2; ++hh)
+          if (lo_[s2][hh] + 4 * n4j > nb) lo_[s2][hh] = nb - 4 * n4j;
+      for (int g = 0; g < n4j; ++g)
+        for (int hh = 0; hh < 2; ++hh)
+          for (int s2 = 0; s2 < 8; ++s2)
+            for (int q = 0; q < 4; ++q) {
+              const int m = 2 * (8 * j + s2) + hh, k = lo_[s2][hh] + 4 * g + q;
+              const bool in = m < D && k >= lo[m] && k < lo[m] + cnt[m];
+              ww.push_back(in ? 0.25f * mel_dense[(size_t)m * nb + k] : 0.f);
+            }
+      for (int s2 = 0; s2 < 8; ++s2) {
+        const int m0 = 2 * (8 * j + s2);
+        wdesc[8 * j + s2] = (uint32_t)(lo_[s2][0] >> 2) | ((uint32_t)(lo_[s2][1] >> 2) << 6) |
+                            (m0 < D ? 0x40000000u : 0u) | (m0 + 1 < D ? 0x80000000u : 0u);
+      }
+      if (n4j > 255) return fail(SPL_ERR_UNSUPPORTED, "spl_create: mel bank too wide");
+      jinfo[j] = (uint32_t)n4j | ((uint32_t)goff << 8);
+      goff += n4j;
+    }
+  }
   // stage-1 twiddles W_N^{n2 k1}
   const int R2 = nfft / 16;
   std::vector<float> twr(R2 * 16), twi(R2 * 16);
@@ -166,7 +206,10 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   const size_t pt_desc = pad4(pw.size()), pt_win = pt_desc + pad4(npairs), pt_tw = pt_win + pad4(Nw);
   const size_t pt_words = pt_tw + 2 * (size_t)nfft;
-  const size_t n_items = pt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  const size_t wt_desc = pad4(ww.size()), wt_jinfo = wt_desc + pad4(wdesc.size()), wt_win = wt_jinfo + pad4(jinfo.size());
+  const size_t wt_tw = wt_win + pad4(Nw), wt_words = wt_tw + 2 * (size_t)nfft;
+  const size_t n_items = pt_words + wt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) +
+                         3 * (size_t)D;
   std::vector<uint32_t> host(n_items, 0u);
   std::memcpy(host.data(), pw.data(), pw.size() * 4);
   std::memcpy(host.data() + pt_desc, pdesc.data(), npairs * 4);
@@ -176,7 +219,15 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
       std::memcpy(host.data() + pt_tw + k1 * R2 + n2, &twr[n2 * 16 + k1], 4);
       std::memcpy(host.data() + pt_tw + nfft + k1 * R2 + n2, &twi[n2 * 16 + k1], 4);
     }
-  size_t o = pt_words;
+  {
+    uint32_t* wt = host.data() + pt_words;  // pt_words is a multiple of 4: the block stays 16-byte aligned
+    std::memcpy(wt, ww.data(), ww.size() * 4);
+    std::memcpy(wt + wt_desc, wdesc.data(), wdesc.size() * 4);
+    std::memcpy(wt + wt_jinfo, jinfo.data(), jinfo.size() * 4);
+    std::memcpy(wt + wt_win, window, Nw * 4);
+    std::memcpy(wt + wt_tw, host.data() + pt_tw, 2 * (size_t)nfft * 4);
+  }
+  size_t o = pt_words + wt_words;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -218,11 +269,23 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.pt_off_win = (int32_t)pt_win;
   h->tab.pt_off_tw = (int32_t)pt_tw;
   h->tab.npairs = npairs;
+  h->tab.wtab = fb + pt_words;
+  h->tab.wtab_words = (int32_t)wt_words;
+  h->tab.wt_off_desc = (int32_t)wt_desc;
+  h->tab.wt_off_jinfo = (int32_t)wt_jinfo;
+  h->tab.wt_off_win = (int32_t)wt_win;
+  h->tab.wt_off_tw = (int32_t)wt_tw;
+  h->tab.nj = nj;
   for (int w = 0; w <= spl::kWarps; ++w) h->tab.pgrp_beg[w] = pgrp[w];
   h->num_sms = 148;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   const char* leg = std::getenv("SPL_LEGACY_KERNEL");
-  h->legacy = leg && leg[0] == '1';
+  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '2') ? leg[0] - '0' : 0;
+  h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words);
+  {  // the warp kernel stages a group's samples inside one pair's exchange planes
+    const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
+    if (h->kernel == 0 && (h->smem_warp > 113 * 1024 || 3 * S + Nw + 4 > 2 * pl)) h->kernel = 2;
+  }
   h->smem_bytes = spl::fbank_smem_bytes(nfft, S, Nw, D, h->D_out, nnz);
   const size_t smem_p = spl::fbank_persistent_smem_bytes(nfft, S, Nw, h->D_out, (int)pt_words);
   if (smem_p > h->smem_bytes) h->smem_bytes = smem_p;
@@ -285,7 +348,9 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   }
   const bool with_noise = h->cfg.dither != 0.f;
   cudaError_t e;
-  if (!h->legacy && a->B <= spl::kMaxPersistentB)
+  if (h->kernel == 0 && a->B <= spl::kMaxPersistentB)
+    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
+  else if (h->kernel != 1 && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
   else
     e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);

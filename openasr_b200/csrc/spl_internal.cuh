@@ -37,6 +37,14 @@ struct Tables {
   int32_t pt_off_desc, pt_off_win, pt_off_tw;  // word offsets inside the block
   int32_t npairs;
   int32_t pgrp_beg[kWarps + 1]; // pairs [pgrp_beg[w], pgrp_beg[w+1]) handled by warp w in the mel phase
+  // warp-pipelined kernel: mel phase with lane = (frame f = lane & 3, slice s = lane >> 2); in
+  // iteration j slice s handles filter pair 8 j + s, all eight pairs padded to n4j groups.
+  //   [weights: float4 index ((goff_j + g) * 2 + half) * 8 + s | pair descriptors (8 per j):
+  //    loA/4 | loB/4 << 6 | validA << 30 | validB << 31 | jinfo: n4j | goff_j << 8 | window | twiddles^T]
+  const float* wtab;
+  int32_t wtab_words;
+  int32_t wt_off_desc, wt_off_jinfo, wt_off_win, wt_off_tw;
+  int32_t nj;
 };
 
 struct FbankParams {
@@ -77,6 +85,9 @@ size_t fbank_smem_bytes(int nfft, int S, int Nw, int D, int D_out, int nnz);
 constexpr int kMaxPersistentB = 512;
 cudaError_t launch_fbank_persistent(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
 size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_words);
+// warp-pipelined kernel: one CTA of 16 independent warps per SM, no block-wide barriers in the loop
+cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
+size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words);
 cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);

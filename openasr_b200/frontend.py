@@ -91,7 +91,7 @@ class FbankHandle:
         a.wav_pitch = wav.stride(0) if B > 1 else wav.shape[1]
         a.wav_cols = wav.shape[1]
         a.sample_format = fmt
-        a.wav_len = wav_len_dev.data_ptr()
+        a.wav_len = wav_len_dev if isinstance(wav_len_dev, int) else wav_len_dev.data_ptr()
         a.B = B
         a.T = T
         a.feats = out.data_ptr()
@@ -139,7 +139,8 @@ def post_inplace(feats: torch.Tensor, feat_len: torch.Tensor, *, cmvn_mode: str 
     a.global_mean = global_mean.data_ptr() if global_mean is not None else None
     a.global_istd = global_istd.data_ptr() if global_istd is not None else None
     a.n_freq_masks, a.n_time_masks = int(n_freq), int(n_time)
-    a.mask_params = mask_params.data_ptr() if mask_params is not None else None
+    a.mask_params = (mask_params if isinstance(mask_params, int) else mask_params.data_ptr()) \
+        if mask_params is not None else None
     with torch.cuda.device(feats.device):
         _capi.check(lib.spl_post_inplace(None, C.byref(a), _stream_ptr(feats.device)), "spl_post_inplace")
 
@@ -202,3 +203,74 @@ def specaug_rectangles(uniforms: torch.Tensor, feat_len: torch.Tensor, T: int, V
         r += 2
         rects.append(resolve(t0s, ts, T))
     return torch.stack(rects, dim=1).to(torch.int32).contiguous()
+
+
+# ---------------------------------------------------------------------- fast host path
+def specaug_rectangles_np(uniforms: np.ndarray, frames: np.ndarray, T: int, V: int, conf: dict) -> np.ndarray:
+    """numpy twin of :func:`specaug_rectangles` for the per-call host path (same float32 arithmetic,
+    same truncation, same slice resolution; ~20x less dispatch overhead than tiny torch ops)."""
+    F_, T_ = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
+    B = uniforms.shape[1]
+    out = np.empty((B, F_ + T_, 2), dtype=np.int32)
+    flen = frames.astype(np.int64)
+
+    def resolve(start, width, size, j):
+        end = start + width
+        s_ = np.clip(np.where(start < 0, start + size, start), 0, size)
+        e_ = np.clip(np.where(end < 0, end + size, end), 0, size)
+        out[:, j, 0] = s_
+        out[:, j, 1] = np.maximum(s_, e_)
+
+    r = 0
+    for j in range(F_):
+        fs = (np.float32(conf["freq_mask_width"]) * uniforms[r]).astype(np.int64)
+        f0s = ((V - fs).astype(np.float32) * uniforms[r + 1]).astype(np.int64)
+        r += 2
+        resolve(f0s, fs, V, j)
+    for j in range(T_):
+        ts = (np.float32(conf["time_mask_width"]) * uniforms[r]).astype(np.int64)
+        t0s = ((flen - ts).astype(np.float32) * uniforms[r + 1]).astype(np.int64)
+        r += 2
+        resolve(t0s, ts, T, F_ + j)
+    return out
+
+
+class HostStager:
+    """Ring of pinned host slots for the few hundred bytes a call uploads (lengths + mask rectangles):
+    one asynchronous H2D per forward instead of several pageable copies.  A slot is reused only after
+    the event recorded behind its copy has completed."""
+
+    def __init__(self, slots: int = 16, nbytes: int = 1 << 14):
+        self._nslots, self._nbytes = slots, nbytes
+        self._slots = None  # pinned memory needs a driver: allocate on first use
+        self._events = [None] * slots
+        self._next = 0
+        self._lock = threading.Lock()
+
+    def upload(self, arrays, device: torch.device) -> Tuple[torch.Tensor, list]:
+        """arrays: list of contiguous numpy arrays (8-byte aligned sizes handled here).
+        Returns (device uint8 tensor keeping the memory alive, list of device pointers)."""
+        sizes = [(a.nbytes + 7) & ~7 for a in arrays]
+        total = sum(sizes)
+        with self._lock:
+            if self._slots is None:
+                self._slots = [torch.empty(self._nbytes, dtype=torch.uint8).pin_memory() for _ in range(self._nslots)]
+            i = self._next
+            self._next = (i + 1) % len(self._slots)
+        if total > self._slots[i].numel():
+            self._slots[i] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
+        if self._events[i] is not None:
+            self._events[i].synchronize()
+        host = self._slots[i].numpy()
+        offs, o = [], 0
+        for a, sz in zip(arrays, sizes):
+            host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            offs.append(o)
+            o += sz
+        dev = torch.empty(total, dtype=torch.uint8, device=device)
+        dev.copy_(self._slots[i][:total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._events[i] = ev
+        base = dev.data_ptr()
+        return dev, [base + x for x in offs]

@@ -84,6 +84,20 @@ def test_specaug_rectangles_equal_reference_slicing():
             assert torch.equal(out, ref)
 
 
+def test_numpy_rectangles_equal_torch_rectangles():
+    from openasr_b200 import frontend
+    lens = torch.tensor([90, 3, 45, 60, 10, 77, 1, 500])
+    for conf in ({"freq_mask_num": 2, "freq_mask_width": 27, "time_mask_num": 2, "time_mask_width": 40},
+                 {"freq_mask_num": 1, "freq_mask_width": 100.0, "time_mask_num": 3, "time_mask_width": 700},
+                 {"freq_mask_num": 0, "freq_mask_width": 5, "time_mask_num": 1, "time_mask_width": 8}):
+        for seed in range(50):
+            torch.manual_seed(seed)
+            u = frontend.specaug_uniforms(8, conf["freq_mask_num"], conf["time_mask_num"])
+            a = frontend.specaug_rectangles(u, lens, 500, 80, conf)
+            b = frontend.specaug_rectangles_np(u.numpy(), lens.numpy(), 500, 80, conf)
+            assert np.array_equal(a.numpy(), b)
+
+
 def test_specaug_uniform_stream_equals_sequential_draws():
     from openasr_b200 import frontend
     torch.manual_seed(4)
