@@ -123,6 +123,12 @@ SPL_API int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream
 SPL_API int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len, int32_t B, int32_t T,
                      int32_t Dm, double* utt_stats, void* stream);
 
+/* tcgen05 building-block self-test: D[128,N] = A[128,K] * B[N,K]^T in kind::tf32 (operands are used
+ * as TF32, i.e. the low 13 mantissa bits are ignored), accumulator in TMEM.  Device pointers;
+ * *status (device int) becomes non-zero if the MMA completion barrier timed out. */
+SPL_API int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t* status,
+                            void* stream);
+
 /* Introspection */
 SPL_API int spl_feature_dim(const spl_handle* h);       /* D_out */
 SPL_API int spl_abi_version(void);

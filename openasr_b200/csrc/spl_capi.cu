@@ -414,4 +414,14 @@ int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len,
   return SPL_OK;
 }
 
+int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t* status, void* stream) {
+  if (!A || !B || !D || !status) return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: null argument");
+  if (N < 16 || N > 256 || (N & 15) || K < 32 || (K & 31) || (size_t)(K / 32) * (128 + N) * 128 > 200 * 1024)
+    return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: need 16 <= N <= 256 (multiple of 16), K multiple of 32, tiles <= 200 KB");
+  cudaError_t e = spl::launch_tc_selftest(A, B, D, N, K, status, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "spl_tc_selftest: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
+}
+
 }  // extern "C"

@@ -92,4 +92,7 @@ cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);
 
+// tcgen05 building-block self-test (tc_selftest.cu)
+cudaError_t launch_tc_selftest(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);
+
 }  // namespace spl

@@ -340,3 +340,24 @@ def test_many_short_utterances_and_large_batches():
                 assert ((norm[i, :m] - want[j, :m]).abs()[:, ok] < 2e-3).all()
             elif m == 1:
                 assert norm[i, :m].abs().max().item() < 1e-3
+
+
+def test_global_cmvn_single_gpu(wavs):
+    """cmvn='global': kernel A's fused fp64 statistics pass + kernel B against the fp64 oracle
+    (the cross-GPU all-reduce is a no-op at world size 1; the gloo test covers N = 2)."""
+    from openasr_b200.cmvn import GlobalCmvn
+    layer, conf = make_layer(cmvn="global")
+    layer.eval()
+    x, lens = pad_batch([wavs[0], wavs[1], wavs[0][:20000]])
+    acc = GlobalCmvn(layer, torch.device("cuda"))
+    acc.update(x.cuda(), lens)
+    acc.update(x[:2].cuda(), lens[:2])          # statistics accumulate across calls
+    mean, istd = acc.finalize()
+    raw, rlen = fo.splayer_forward(x, lens, dict(conf, cmvn="none"))
+    st = fo.cmvn_stats(raw, rlen.tolist()) + fo.cmvn_stats(raw[:2], rlen[:2].tolist())
+    assert abs(acc.stats[-1].item() - st[2, 0].item()) < 0.5
+    assert torch.allclose(mean.cpu(), st[0] / st[2], atol=2e-5)
+    feats, flen = layer(x.cuda(), lens)
+    ref, _ = fo.splayer_forward(x, lens, conf, global_stats=st)
+    close(feats, ref, scale=(istd.cpu().float().clamp_min(1.0))[None, None, :])
+    assert len(layer.state_dict()) == 0
