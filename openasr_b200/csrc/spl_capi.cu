@@ -190,6 +190,92 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
       goff += n4j;
     }
   }
+  // ---- tcgen05 DFT-as-GEMM tables (see spl_internal.cuh / fbank_tc.cu) ----
+  const int half = nfft / 4, units = nfft / 32;
+  auto tf32_rn = [](double v) {  // nearest TF32 (10 explicit mantissa bits), returned as float
+    float f = (float)v;
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);  // round to nearest even on the 13 dropped bits
+    u &= 0xFFFFE000u;
+    std::memcpy(&f, &u, 4);
+    return f;
+  };
+  std::vector<float> tcb((size_t)units * 8 * half * 8);
+  for (int u = 0; u < units; ++u)
+    for (int blk = 0; blk < 4; ++blk)
+      for (int n = 0; n < half; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int jp = 8 * u + e, j = 2 * jp + (blk & 1), k = n + 1;
+          const double ang = 2.0 * M_PI * (double)((long)j * k % nfft) / (double)nfft;
+          const double v = blk < 2 ? std::cos(ang) : std::sin(ang);
+          const float hi = tf32_rn(v), lo = tf32_rn(v - (double)hi);
+          // SWIZZLE_32B K-major tile of [half x 8]: byte offset r*32 + ((c>>2 ^ r>>2)&1)*16 + (c&3)*4
+          const size_t off = (size_t)(n * 32 + ((((e >> 2) ^ (n >> 2)) & 1) << 4) + ((e & 3) << 2)) / 4;
+          const size_t tile = (size_t)half * 8;
+          tcb[((size_t)u * 8 + blk * 2 + 0) * tile + off] = hi;
+          tcb[((size_t)u * 8 + blk * 2 + 1) * tile + off] = lo;
+        }
+  // mel segments over the split power layout: array 0 index n <-> bin n+1, array 1 index n <-> bin nb-1-n
+  std::vector<float> sw;
+  std::vector<uint32_t> sdesc;  // pairs (x, y)
+  std::vector<int> scost, sfilt;
+  for (int m = 0; m < D; ++m) {
+    struct Run { int arr, i0, i1; };
+    Run runs[2];
+    int nr = 0;
+    if (cnt[m] > 0) {
+      const int b0 = lo[m], b1 = lo[m] + cnt[m] - 1;  // bins (>= 1, <= nb-1)
+      if (b0 <= half) runs[nr++] = {0, (b0 < 1 ? 1 : b0) - 1, (b1 < half ? b1 : half) - 1};
+      if (b1 > half) runs[nr++] = {1, nb - 1 - b1, nb - 1 - (b0 > half + 1 ? b0 : half + 1)};
+    }
+    if (nr == 0) runs[nr++] = {0, 0, -1};  // empty filter: one zero-length segment -> log(eps)
+    for (int r = 0; r < nr; ++r) {
+      int start4 = runs[r].i0 & ~3;
+      int n4 = runs[r].i1 >= runs[r].i0 ? (runs[r].i1 - start4 + 4) / 4 : 0;
+      if (start4 + 4 * n4 > half) start4 = half - 4 * n4;
+      const uint32_t woff4 = (uint32_t)(sw.size() / 4);
+      for (int i = 0; i < 4 * n4; ++i) {
+        const int idx = start4 + i;
+        const int bin = runs[r].arr == 0 ? idx + 1 : nb - 1 - idx;
+        const bool in = idx >= runs[r].i0 && idx <= runs[r].i1 && bin >= lo[m] && bin < lo[m] + cnt[m];
+        sw.push_back(in ? mel_dense[(size_t)m * nb + bin] : 0.f);
+      }
+      sdesc.push_back((uint32_t)(start4 >> 2) | ((uint32_t)n4 << 6) | ((uint32_t)runs[r].arr << 12) |
+                      ((r == 0 ? 1u : 0u) << 13) | ((r == nr - 1 ? 1u : 0u) << 14) | ((uint32_t)m << 16));
+      sdesc.push_back(woff4);
+      scost.push_back(10 + 6 * n4 + (r == nr - 1 ? 8 : 0));
+      sfilt.push_back(m);
+    }
+  }
+  const int nseg = (int)scost.size();
+  int32_t sgrp[5];
+  {
+    long total = 0;
+    for (int i = 0; i < nseg; ++i) total += scost[i];
+    int i = 0;
+    long acc = 0;
+    sgrp[0] = 0;
+    for (int g = 1; g < 4; ++g) {
+      const long target = total * g / 4;
+      while (i < nseg && (acc + scost[i] / 2 < target || (i > 0 && sfilt[i] == sfilt[i - 1]))) acc += scost[i++];
+      sgrp[g] = i;
+    }
+    sgrp[4] = nseg;
+  }
+  // DFT of the window (dither-mean correction): Wc[k] = sum w_j cos, Ws[k] = sum w_j sin, k = 0..nb-1
+  std::vector<float> wc(nb), wsn(nb);
+  for (int k = 0; k < nb; ++k) {
+    double c = 0, s_ = 0;
+    for (int j = 0; j < Nw; ++j) {
+      const double ang = 2.0 * M_PI * (double)((long)j * k % nfft) / (double)nfft;
+      c += (double)window[j] * std::cos(ang);
+      s_ += (double)window[j] * std::sin(ang);
+    }
+    wc[k] = (float)c;
+    wsn[k] = (float)s_;
+  }
+
   // stage-1 twiddles W_N^{n2 k1}
   const int R2 = nfft / 16;
   std::vector<float> twr(R2 * 16), twi(R2 * 16);
@@ -208,8 +294,11 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   const size_t pt_words = pt_tw + 2 * (size_t)nfft;
   const size_t wt_desc = pad4(ww.size()), wt_jinfo = wt_desc + pad4(wdesc.size()), wt_win = wt_jinfo + pad4(jinfo.size());
   const size_t wt_tw = wt_win + pad4(Nw), wt_words = wt_tw + 2 * (size_t)nfft;
-  const size_t n_items = pt_words + wt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) +
-                         3 * (size_t)D;
+  const size_t tt_desc = pad4(sw.size()), tt_win = tt_desc + pad4(sdesc.size()), tt_wc = tt_win + pad4(Nw);
+  const size_t tt_ws = tt_wc + pad4(nb), tt_words = tt_ws + pad4(nb);
+  const size_t tcb_words = tcb.size();  // multiple of 4
+  const size_t n_items = pt_words + wt_words + tt_words + tcb_words + (size_t)Nw + 2 * (size_t)R2 * 16 +
+                         (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
   std::vector<uint32_t> host(n_items, 0u);
   std::memcpy(host.data(), pw.data(), pw.size() * 4);
   std::memcpy(host.data() + pt_desc, pdesc.data(), npairs * 4);
@@ -227,7 +316,16 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     std::memcpy(wt + wt_win, window, Nw * 4);
     std::memcpy(wt + wt_tw, host.data() + pt_tw, 2 * (size_t)nfft * 4);
   }
-  size_t o = pt_words + wt_words;
+  {
+    uint32_t* tt = host.data() + pt_words + wt_words;
+    std::memcpy(tt, sw.data(), sw.size() * 4);
+    std::memcpy(tt + tt_desc, sdesc.data(), sdesc.size() * 4);
+    std::memcpy(tt + tt_win, window, Nw * 4);
+    std::memcpy(tt + tt_wc, wc.data(), nb * 4);
+    std::memcpy(tt + tt_ws, wsn.data(), nb * 4);
+    std::memcpy(tt + tt_words, tcb.data(), tcb_words * 4);
+  }
+  size_t o = pt_words + wt_words + tt_words + tcb_words;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -276,11 +374,20 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.wt_off_win = (int32_t)wt_win;
   h->tab.wt_off_tw = (int32_t)wt_tw;
   h->tab.nj = nj;
+  h->tab.tc_tab = fb + pt_words + wt_words;
+  h->tab.tc_b = fb + pt_words + wt_words + tt_words;
+  h->tab.tc_tab_words = (int32_t)tt_words;
+  h->tab.tc_off_desc = (int32_t)tt_desc;
+  h->tab.tc_off_win = (int32_t)tt_win;
+  h->tab.tc_off_wc = (int32_t)tt_wc;
+  h->tab.tc_off_ws = (int32_t)tt_ws;
+  h->tab.tc_nseg = nseg;
+  for (int g = 0; g < 5; ++g) h->tab.tc_sgrp_beg[g] = sgrp[g];
   for (int w = 0; w <= spl::kWarps; ++w) h->tab.pgrp_beg[w] = pgrp[w];
   h->num_sms = 148;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   const char* leg = std::getenv("SPL_LEGACY_KERNEL");
-  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '2') ? leg[0] - '0' : 0;
+  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '3') ? leg[0] - '0' : 0;  // 3: tcgen05 DFT-as-GEMM (experimental)
   h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words);
   {  // the warp kernel stages a group's samples inside one pair's exchange planes
     const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
@@ -348,9 +455,12 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   }
   const bool with_noise = h->cfg.dither != 0.f;
   cudaError_t e;
-  if (h->kernel == 0 && a->B <= spl::kMaxPersistentB)
+  if (h->kernel == 3 && a->B <= spl::kMaxPersistentB && a->sample_format == SPL_SAMPLES_F32 && h->cfg.dither == 0.f &&
+      h->cfg.window_size * 2 > h->cfg.padded_size)
+    e = spl::launch_fbank_tc(p, h->cfg.padded_size, with_noise, h->num_sms, st);
+  else if ((h->kernel == 0 || h->kernel == 3) && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
-  else if (h->kernel != 1 && a->B <= spl::kMaxPersistentB)
+  else if (h->kernel == 2 && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
   else
     e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
@@ -416,9 +526,11 @@ int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len,
 
 int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t* status, void* stream) {
   if (!A || !B || !D || !status) return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: null argument");
-  if (N < 16 || N > 256 || (N & 15) || K < 32 || (K & 31) || (size_t)(K / 32) * (128 + N) * 128 > 200 * 1024)
-    return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: need 16 <= N <= 256 (multiple of 16), K multiple of 32, tiles <= 200 KB");
-  cudaError_t e = spl::launch_tc_selftest(A, B, D, N, K, status, static_cast<cudaStream_t>(stream));
+  if (N < 16 || N > 256 || (N & 15) || K < 8 || (K & 7) || (size_t)K * (128 + N) * 4 > 200 * 1024)
+    return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: need 16 <= N <= 256 (multiple of 16), K multiple of 8, tiles <= 200 KB");
+  // K not a multiple of 32 selects the SWIZZLE_32B variant (one 8-wide tile per K step)
+  cudaError_t e = (K & 31) ? spl::launch_tc_selftest_sw32(A, B, D, N, K, status, static_cast<cudaStream_t>(stream))
+                           : spl::launch_tc_selftest(A, B, D, N, K, status, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "spl_tc_selftest: launch");
   g_launches.fetch_add(1);
   return SPL_OK;

@@ -45,6 +45,17 @@ struct Tables {
   int32_t wtab_words;
   int32_t wt_off_desc, wt_off_jinfo, wt_off_win, wt_off_tw;
   int32_t nj;
+  // tcgen05 DFT-as-GEMM kernel (fbank_tc.cu).  HALF = Nfft/4 outputs / inputs per folded block.
+  //   tc_b   : twiddle operand images, [Nfft/32 units][4 blocks: cos-even, cos-odd, sin-even, sin-odd]
+  //            [hi, lo][HALF n x 8 k tf32, K-major SWIZZLE_32B] -- copied to shared memory verbatim
+  //   tc_tab : [segment weights | segment descriptors (uint2) | window | Wc | Ws], one TMA bulk copy
+  //   segment descriptor .x: start/4 | n4 << 6 | array (0: bins 1..HALF, 1: mirrored bins) << 12 |
+  //            first << 13 | last << 14 | filter << 16 ;  .y: weight offset / 4
+  const float* tc_b;
+  const float* tc_tab;
+  int32_t tc_tab_words, tc_off_desc, tc_off_win, tc_off_wc, tc_off_ws;
+  int32_t tc_nseg;
+  int32_t tc_sgrp_beg[5];
 };
 
 struct FbankParams {
@@ -92,7 +103,12 @@ cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);
 
+// tcgen05 DFT-as-GEMM fbank kernel (fp32 samples, B <= kMaxPersistentB); one CTA per SM
+cudaError_t launch_fbank_tc(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
+size_t fbank_tc_smem_bytes(int nfft, int D_out, int tc_tab_words);
+
 // tcgen05 building-block self-test (tc_selftest.cu)
+cudaError_t launch_tc_selftest_sw32(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);
 
 }  // namespace spl

@@ -21,6 +21,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
          | ((uint64_t)2 << 61);                                   // SWIZZLE_128B
 }
 
+// K-major SWIZZLE_32B tile: rows of 32 bytes (8 tf32 = one kind::tf32 K step), 8-row groups of
+// 256 bytes, the two 16-byte chunks of a row swapped when bit 7 of the byte address is set
+// (Swizzle<1,4,3>), i.e. for rows 4..7 of every group.  Tile start 256-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);  // SWIZZLE_32B
+}
+__device__ __host__ __forceinline__ uint32_t sw32_offset(int r, int c /* 0..7 */) {
+  return (uint32_t)(r * 32 + ((((c >> 2) ^ (r >> 2)) & 1) << 4) + ((c & 3) << 2));
+}
+
 // byte offset of element (row r, 32-bit column c in [0, 32)) inside a SWIZZLE_128B K-major tile
 __device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 2) ^ (r & 7)) & 7) << 4) + ((c & 3) << 2));

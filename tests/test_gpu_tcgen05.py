@@ -12,7 +12,8 @@ def _tf32(x):  # what the tensor core sees: low 13 mantissa bits dropped
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-@pytest.mark.parametrize("N,K", [(128, 32), (128, 128), (64, 96), (256, 64), (16, 32)])
+@pytest.mark.parametrize("N,K", [(128, 32), (128, 128), (64, 96), (256, 64), (16, 32),
+                                 (128, 8), (128, 24), (64, 40), (256, 72)])  # K % 32 != 0: SWIZZLE_32B tiles
 def test_tcgen05_tf32_gemm_selftest(N, K):
     from openasr_b200 import _capi
     lib = _capi.load()
@@ -29,3 +30,38 @@ def test_tcgen05_tf32_gemm_selftest(N, K):
     ref = A.double() @ B.double().t()
     err = (D.double() - ref).abs().max().item()
     assert err < 1e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def _pad_batch(ws):
+    lens = [w.shape[0] for w in ws]
+    x = torch.zeros(len(ws), max(lens))
+    for i, w in enumerate(ws):
+        x[i, :lens[i]] += w
+    return x, lens
+
+
+@pytest.mark.parametrize("sr,D,energy", [(16000, 80, False), (16000, 40, True), (8000, 40, False)])
+def test_tcgen05_dft_kernel_matches_oracle(monkeypatch, wavs, sr, D, energy):
+    """The DFT-as-GEMM variant of kernel A (3xTF32 on tcgen05, SPL_LEGACY_KERNEL=3) on real speech:
+    same tolerance as the FFT kernels (|d| <= 1e-3 + 1e-4 |ref|), exact lengths and zero padding."""
+    from oracle import frontend_oracle as fo
+    from openasr_b200 import SPLayer
+    monkeypatch.setenv("SPL_LEGACY_KERNEL", "3")
+    dec = 16000 // sr
+    x, lens = _pad_batch([wavs[0][::dec].contiguous(), wavs[1][::dec].contiguous(), wavs[0][::dec][:7001].contiguous()])
+    conf = {"feature_type": "fbank", "sample_rate": sr, "num_mel_bins": D, "use_energy": energy, "dither": 0.0}
+    layer = SPLayer(conf).cuda().eval()
+    feats, flen = layer(x.cuda(), lens)
+    torch.cuda.synchronize()
+    ref, rlen = fo.splayer_forward(x, lens, conf)
+    ref64, _ = fo.splayer_forward(x, lens, conf, dtype=torch.float64)
+    assert torch.equal(flen.cpu(), rlen)
+    f = feats.cpu()
+    assert torch.isfinite(f).all()
+    d = (f - ref).abs()
+    tol = 1e-3 + 1e-4 * ref.abs() + 2.0 * (ref.double() - ref64).abs().float()
+    print("tcgen05 DFT: max|d| vs ref32 %.3g, vs fp64 %.3g (ref32 vs fp64 %.3g)" % (
+        d.max().item(), (f.double() - ref64).abs().max().item(), (ref.double() - ref64).abs().max().item()))
+    assert (d <= tol).all(), "max|d|=%g" % d.max().item()
+    for i, m in enumerate(rlen.tolist()):
+        assert (f[i, m:] == 0).all()
