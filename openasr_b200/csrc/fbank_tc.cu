@@ -22,8 +22,8 @@
 
 namespace spl {
 
-constexpr int kTcWarps = 16;
-constexpr int kTcThreads = kTcWarps * 32;
+constexpr int kTcWarps = 16;                       // producer / epilogue warps
+constexpr int kTcThreads = (kTcWarps + 1) * 32;    // + one warp whose lane 0 issues TMA and MMAs
 constexpr int kTcRows = 128;
 
 struct TLayout {  // byte offsets
@@ -49,7 +49,7 @@ __host__ __device__ inline TLayout make_tlayout(int nfft, int D_out, int tab_wor
   // per-row arrays: mu'[128] z_half[128] energy[128] sumg[128] (float) | src offset[128] (int64) | b[128] t[128] (int)
   L.off_fpre = L.off_rows + 128 * 4 * 4 + 128 * 8 + 128 * 4 * 2;
   L.off_bar = (L.off_fpre + (kMaxPersistentB + 1) * 4 + 7) & ~7;
-  L.total = L.off_bar + 8 * 8;
+  L.total = L.off_bar + 10 * 8;
   return L;
 }
 
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
   int* r_b = reinterpret_cast<int*>(r_src + 128);
   int* r_t = r_b + 128;
   int* fpre = reinterpret_cast<int*>(sm + L.off_fpre);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.off_bar);  // [0] tables, [1..2] B landed, [3..4] MMAs done
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.off_bar);  // [0] tables, [1..2] B landed, [3..4] MMAs done, [5..6] A written
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* wav = static_cast<const float*>(p.wav);
@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
   // ---- 0. tables (TMA), frame prefix (warp 0), TMEM (warp 1), barriers --------------------------
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+    mbar_init(bars + 5, kTcWarps);
+    mbar_init(bars + 6, kTcWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bars, (uint32_t)p.tab.tc_tab_words * 4u);
     bulk_g2s(sm + L.off_tab, p.tab.tc_tab, (uint32_t)p.tab.tc_tab_words * 4u, bars);
@@ -171,111 +173,185 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
   for (int pos = r0; pos < r1; pos += kTcRows) {
     const int nrows = r1 - pos < kTcRows ? r1 - pos : kTcRows;
 
-    // ---- 1. row table + per-row mean / energy / z_{N/2} (warp per row) ---------------------------
-    for (int r = w; r < kTcRows; r += kTcWarps) {
-      const int g = pos + (r < nrows ? r : 0);  // invalid rows mirror row 0 (finite data, never stored)
-      int lo = 0, hi = B - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (fpre[mid] <= g) lo = mid; else hi = mid - 1;
+    // ---- 1. row table + per-row mean / energy / z_{N/2} (warp per row).  Pass A locates the rows and
+    //      prefetches their samples into L2 (first touch comes from HBM); pass B reduces them. ----------
+    if (w < kTcWarps) {
+      int bh = 0;
+      {
+        const int g0 = pos + (w < nrows ? w : 0);
+        int lo = 0, hi = B - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (fpre[mid] <= g0) lo = mid; else hi = mid - 1;
+        }
+        bh = lo;
       }
-      const int b = lo, t = g - fpre[lo];
-      const long long src = (long long)b * p.wav_pitch + (long long)t * S;
-      const float* x = wav + src;
-      float v[16];
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = lane + 32 * i;
-        v[i] = j < Nw ? __ldg(x + j) : 0.f;
-        sum += v[i];
+      for (int r = w; r < kTcRows; r += kTcWarps) {
+        const bool valid = r < nrows;
+        const int g = pos + (valid ? r : 0);  // invalid rows mirror row 0 (finite data, never stored)
+        int b = valid ? bh : 0;
+        if (!valid) {
+          int lo = 0, hi = B - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (fpre[mid] <= g) lo = mid; else hi = mid - 1;
+          }
+          b = lo;
+        } else {
+          while (fpre[b + 1] <= g) ++b;
+          bh = b;
+        }
+        const int t = g - fpre[b];
+        const long long src = (long long)b * p.wav_pitch + (long long)t * S;
+        if (32 * lane < Nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(wav + src + 32 * lane));
+        if (lane == 0) {
+          r_src[r] = src;
+          r_b[r] = b;
+          r_t[r] = t;
+        }
       }
-      float mean = 0.f;
-      if (p.remove_dc) mean = group_sum(sum, 32) * (1.0f / (float)Nw);
-      float e = 0.f;
-      if (p.use_energy) {
+      __syncwarp();
+      for (int r = w; r < kTcRows; r += kTcWarps) {
+        const float* x = wav + r_src[r];
+        float v[16];
+        float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float d = (lane + 32 * i < Nw) ? v[i] - mean : 0.f;
-          e = fmaf(d, d, e);
+          const int j = lane + 32 * i;
+          v[i] = j < Nw ? __ldg(x + j) : 0.f;
         }
-        e = group_sum(e, 32);
-      }
-      if (lane == 0) {
-        const float mu = (1.0f - c) * mean;
-        r_mu[r] = mu;
-        r_en[r] = __logf(fmaxf(e, kEps));
-        r_sg[r] = 0.f;
-        r_zh[r] = NB < Nw ? win[NB] * (__ldg(x + NB) - c * __ldg(x + NB - 1) - mu) : 0.f;
-        r_src[r] = src;
-        r_b[r] = b;
-        r_t[r] = t;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += v[i];
+        float mean = 0.f;
+        if (p.remove_dc) mean = group_sum(sum, 32) * (1.0f / (float)Nw);
+        float e = 0.f;
+        if (p.use_energy) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float d = (lane + 32 * i < Nw) ? v[i] - mean : 0.f;
+            e = fmaf(d, d, e);
+          }
+          e = group_sum(e, 32);
+        }
+        // z_{N/2}: x[N/2] sits in lane 0 (i = N/64), x[N/2 - 1] in lane 31 (i = N/64 - 1)
+        const float xh = v[NB / 32], xhm = __shfl_sync(0xffffffffu, v[NB / 32 - 1], 31);
+        if (lane == 0) {
+          const float mu = (1.0f - c) * mean;
+          r_mu[r] = mu;
+          r_en[r] = __logf(fmaxf(e, kEps));
+          r_sg[r] = 0.f;
+          r_zh[r] = NB < Nw ? win[NB] * (xh - c * xhm - mu) : 0.f;
+        }
       }
     }
     __syncthreads();
 
-    // ---- 2. K loop: build A chunk u (all warps) while the tensor core consumes chunk u-1 ----------
-    const int i8 = tid & 7;
-    for (int u = 0; u < UNITS; ++u) {
-      const int s = u & 1;
-      uint8_t* stage = sm + (size_t)s * L.stage_bytes;
-      if (use_cnt[s] > 0) {  // MMAs that read this stage (two chunks ago) must be complete
-        if (!tc::mbar_wait_bounded(bars + 3 + s, (use_cnt[s] - 1) & 1)) failed = true;
-      }
-      if (tid == 0) {  // twiddle images of chunk u -> stage (one bulk copy: 8 tiles)
-        mbar_expect_tx(bars + 1 + s, 8u * (uint32_t)L.b_tile);
-        bulk_g2s(stage + 8 * L.a_tile, reinterpret_cast<const uint8_t*>(p.tab.tc_b) + (size_t)u * 8 * L.b_tile,
-                 8u * (uint32_t)L.b_tile, bars + 1 + s);
-      }
-      const int j = 16 * u + 2 * i8;  // this thread's even index; j+1 is the odd one
-      const int m = NFFT - j;         // mirror of j; m-1 mirrors j+1
-      const float wj0 = j < Nw ? win[j] : 0.f, wj1 = j + 1 < Nw ? win[j + 1] : 0.f;
-      const float wm0 = m < Nw ? win[m] : 0.f, wm1 = m - 1 < Nw ? win[m - 1] : 0.f;
+    // ---- 2. K loop, warp specialised: 16 producer warps build the A operand of chunk u (fold + hi/lo
+    //      split, samples prefetched one chunk ahead in registers) and arrive on full[s]; lane 0 of the
+    //      17th warp streams the twiddle images (TMA) and issues the MMAs, whose commit frees the stage.
+    if (w < kTcWarps) {
+      const int i8 = tid & 7;
+      const float* xr[2];
+      float mur[2];
+      uint32_t offr[2];
 #pragma unroll
-      for (int it = 0; it < kTcRows * 8 / kTcThreads; ++it) {
-        const int r = (tid >> 3) + it * (kTcThreads / 8);
-        const float* x = wav + r_src[r];
-        const float mu = r_mu[r];
-        // z_j = w_j (x_j - c x_{j-1} - (1-c) mean), x_{-1} := x_0 ; zero beyond the window
-        const float xjm = __ldg(x + (j > 0 ? j - 1 : 0)), xj0 = __ldg(x + j), xj1 = (j + 1 < Nw) ? __ldg(x + j + 1) : 0.f;
-        const float zj0 = wj0 * (xj0 - c * xjm - mu);
-        const float zj1 = wj1 * (xj1 - c * xj0 - mu);
-        float zm0 = 0.f, zm1 = 0.f;
-        if (m - 1 < Nw) {  // mirrors inside the window (m >= N/2 + 2 > 1)
-          const float xm2 = __ldg(x + m - 2), xm1 = __ldg(x + m - 1);
-          zm1 = wm1 * (xm1 - c * xm2 - mu);
-          if (m < Nw) zm0 = wm0 * (__ldg(x + m) - c * xm1 - mu);
-        }
-        const float vals[4] = {zj0 + zm0, zj1 + zm1, zj0 - zm0, zj1 - zm1};  // ce, co, se, so entries
-        const uint32_t off = tc::sw32_offset(r, i8);
-#pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          const float hi = __uint_as_float(__float_as_uint(vals[blk]) & 0xFFFFE000u);
-          *reinterpret_cast<float*>(stage + (blk * 2 + 0) * L.a_tile + off) = hi;
-          *reinterpret_cast<float*>(stage + (blk * 2 + 1) * L.a_tile + off) = vals[blk] - hi;
-        }
+      for (int it = 0; it < 2; ++it) {
+        const int r = (tid >> 3) + it * 64;
+        xr[it] = wav + r_src[r];
+        mur[it] = r_mu[r];
+        offr[it] = tc::sw32_offset(r, i8);
       }
-      fence_proxy_async();  // generic-proxy writes of the A tiles -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        if (!tc::mbar_wait_bounded(bars + 1 + s, use_cnt[s] & 1)) failed = true;
-        tc::fence_after_sync();
+      float nx[2][6];
+      auto load_unit = [&](int u, float (&dst)[2][6]) {
+        const int j = 16 * u + 2 * i8, m = NFFT - j;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const float* x = xr[it];
+          dst[it][0] = __ldg(x + (j > 0 ? j - 1 : 0));
+          dst[it][1] = __ldg(x + j);
+          dst[it][2] = __ldg(x + j + 1);              // j + 1 <= N/2 - 1 < Nw
+          dst[it][3] = (m - 1 < Nw) ? __ldg(x + m - 2) : 0.f;
+          dst[it][4] = (m - 1 < Nw) ? __ldg(x + m - 1) : 0.f;
+          dst[it][5] = (m < Nw) ? __ldg(x + m) : 0.f;
+        }
+      };
+      load_unit(0, nx);
+#pragma unroll 1
+      for (int u = 0; u < UNITS; ++u) {
+        const int s = u & 1;
+        uint8_t* stage = sm + (size_t)s * L.stage_bytes;
+        float cur[2][6];
+#pragma unroll
+        for (int it = 0; it < 2; ++it)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) cur[it][q] = nx[it][q];
+        if (u + 1 < UNITS) load_unit(u + 1, nx);
+        const int j = 16 * u + 2 * i8, m = NFFT - j;
+        const float wj0 = win[j], wj1 = win[j + 1];
+        const float wm0 = m < Nw ? win[m] : 0.f, wm1 = m - 1 < Nw ? win[m - 1] : 0.f;
+        if (use_cnt[s] > 0 && !tc::mbar_wait_bounded(bars + 3 + s, (use_cnt[s] - 1) & 1)) failed = true;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const float mu = mur[it];
+          // z_j = w_j (x_j - c x_{j-1} - (1-c) mean), x_{-1} := x_0 ; zero beyond the window
+          const float zj0 = wj0 * (cur[it][1] - c * cur[it][0] - mu);
+          const float zj1 = wj1 * (cur[it][2] - c * cur[it][1] - mu);
+          const float zm1 = wm1 * (cur[it][4] - c * cur[it][3] - mu);
+          const float zm0 = wm0 * (cur[it][5] - c * cur[it][4] - mu);
+          const float v0 = zj0 + zm0, v1 = zj1 + zm1, v2 = zj0 - zm0, v3 = zj1 - zm1;  // ce, co, se, so entries
+          uint8_t* dstp = stage + offr[it];
+          const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
+          const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+          const float h2 = __uint_as_float(__float_as_uint(v2) & 0xFFFFE000u);
+          const float h3 = __uint_as_float(__float_as_uint(v3) & 0xFFFFE000u);
+          *reinterpret_cast<float*>(dstp + 0 * L.a_tile) = h0;
+          *reinterpret_cast<float*>(dstp + 1 * L.a_tile) = v0 - h0;
+          *reinterpret_cast<float*>(dstp + 2 * L.a_tile) = h1;
+          *reinterpret_cast<float*>(dstp + 3 * L.a_tile) = v1 - h1;
+          *reinterpret_cast<float*>(dstp + 4 * L.a_tile) = h2;
+          *reinterpret_cast<float*>(dstp + 5 * L.a_tile) = v2 - h2;
+          *reinterpret_cast<float*>(dstp + 6 * L.a_tile) = h3;
+          *reinterpret_cast<float*>(dstp + 7 * L.a_tile) = v3 - h3;
+        }
+        fence_proxy_async();  // generic-proxy writes of the A tiles -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_addr(bars + 5 + s)) : "memory");
+        use_cnt[s] += 1;
+      }
+    } else {
+      if (lane == 0) {
         const uint32_t idesc = tc::make_idesc_tf32(HALF);
-        const uint32_t abase = tc::smem_addr(stage), bbase = abase + 8 * L.a_tile;
+#pragma unroll 1
+        for (int u = 0; u < UNITS; ++u) {
+          const int s = u & 1;
+          uint8_t* stage = sm + (size_t)s * L.stage_bytes;
+          if (use_cnt[s] > 0 && !tc::mbar_wait_bounded(bars + 3 + s, (use_cnt[s] - 1) & 1)) failed = true;
+          mbar_expect_tx(bars + 1 + s, 8u * (uint32_t)L.b_tile);
+          bulk_g2s(stage + 8 * L.a_tile, reinterpret_cast<const uint8_t*>(p.tab.tc_b) + (size_t)u * 8 * L.b_tile,
+                   8u * (uint32_t)L.b_tile, bars + 1 + s);
+          if (!tc::mbar_wait_bounded(bars + 5 + s, use_cnt[s] & 1)) failed = true;
+          if (!tc::mbar_wait_bounded(bars + 1 + s, use_cnt[s] & 1)) failed = true;
+          tc::fence_after_sync();
+          const uint32_t abase = tc::smem_addr(stage), bbase = abase + 8 * L.a_tile;
 #pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          const uint64_t ahi = tc::make_desc_sw32(abase + (blk * 2 + 0) * L.a_tile);
-          const uint64_t alo = tc::make_desc_sw32(abase + (blk * 2 + 1) * L.a_tile);
-          const uint64_t bhi = tc::make_desc_sw32(bbase + (blk * 2 + 0) * L.b_tile);
-          const uint64_t blo = tc::make_desc_sw32(bbase + (blk * 2 + 1) * L.b_tile);
-          const uint32_t d = tmem + blk * HALF;
-          tc::mma_tf32(d, ahi, bhi, idesc, u > 0);
-          tc::mma_tf32(d, alo, bhi, idesc, 1);
-          tc::mma_tf32(d, ahi, blo, idesc, 1);
+          for (int blk = 0; blk < 4; ++blk) {
+            const uint64_t ahi = tc::make_desc_sw32(abase + (blk * 2 + 0) * L.a_tile);
+            const uint64_t alo = tc::make_desc_sw32(abase + (blk * 2 + 1) * L.a_tile);
+            const uint64_t bhi = tc::make_desc_sw32(bbase + (blk * 2 + 0) * L.b_tile);
+            const uint64_t blo = tc::make_desc_sw32(bbase + (blk * 2 + 1) * L.b_tile);
+            const uint32_t d = tmem + blk * HALF;
+            tc::mma_tf32(d, ahi, bhi, idesc, u > 0);
+            tc::mma_tf32(d, alo, bhi, idesc, 1);
+            tc::mma_tf32(d, ahi, blo, idesc, 1);
+          }
+          tc::commit(bars + 3 + s);
+          use_cnt[s] += 1;
         }
-        tc::commit(bars + 3 + s);
+      } else {
+        use_cnt[0] += (UNITS + 1) / 2;
+        use_cnt[1] += UNITS / 2;
       }
-      use_cnt[s] += 1;
+      __syncwarp();
     }
     // all MMAs of the tile complete (commits arrive in order; wait for the last use of both stages)
     for (int s = 0; s < 2; ++s)
@@ -284,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
     __syncthreads();  // every thread is past its last stage access: the power arrays may overwrite them
 
     // ---- 3. epilogue A: TMEM -> power spectrum -> shared memory -------------------------------------
-    {
+    if (w < kTcWarps) {
       const int q = w & 3, cpart = w >> 2;  // TMEM lane quarter, column part
       const int row = 32 * q + lane;
       const float zh = r_zh[row];
@@ -322,37 +398,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
     tc::fence_after_sync();
 
     // ---- 4. epilogue B: mel segments, lane = row, warp = (row group, segment group) -------------------
-    {
+    if (w < kTcWarps) {
       const int rg = w & 3, cg = w >> 2;
       const int row = 32 * rg + lane;
-      const float4* pr[2] = {reinterpret_cast<const float4*>(parr + (size_t)row * L.pp),
-                             reinterpret_cast<const float4*>(parr + (size_t)(kTcRows + row) * L.pp)};
+      const float4* pr0 = reinterpret_cast<const float4*>(parr + (size_t)row * L.pp);
+      const float4* pr1 = reinterpret_cast<const float4*>(parr + (size_t)(kTcRows + row) * L.pp);
       float* orow = out_stage + row * L.op + (p.use_energy ? 1 : 0);
       float acc0 = 0.f, acc1 = 0.f;
       for (int sidx = p.tab.tc_sgrp_beg[cg]; sidx < p.tab.tc_sgrp_beg[cg + 1]; ++sidx) {
         const uint2 d = segd[sidx];
-        const float4* pp4 = pr[(d.x >> 12) & 1] + (d.x & 63u);
+        const float4* pp4 = ((d.x >> 12) & 1 ? pr1 : pr0) + (d.x & 63u);
         const float4* wv = segw + d.y;
         const int n4 = (d.x >> 6) & 63u;
         if (d.x & (1u << 13)) acc0 = acc1 = 0.f;
-        int g = 0;
-        for (; g + 1 < n4; g += 2) {
-          const float4 pa = pp4[g], pb = pp4[g + 1], wa = wv[g], wb = wv[g + 1];
-          acc0 = fmaf(pa.x, wa.x, acc0);
-          acc1 = fmaf(pb.x, wb.x, acc1);
-          acc0 = fmaf(pa.y, wa.y, acc0);
-          acc1 = fmaf(pb.y, wb.y, acc1);
-          acc0 = fmaf(pa.z, wa.z, acc0);
-          acc1 = fmaf(pb.z, wb.z, acc1);
-          acc0 = fmaf(pa.w, wa.w, acc0);
-          acc1 = fmaf(pb.w, wb.w, acc1);
-        }
-        if (g < n4) {
+#pragma unroll 1
+        for (int g = 0; g < n4; ++g) {
           const float4 pa = pp4[g], wa = wv[g];
           acc0 = fmaf(pa.x, wa.x, acc0);
-          acc0 = fmaf(pa.y, wa.y, acc0);
+          acc1 = fmaf(pa.y, wa.y, acc1);
           acc0 = fmaf(pa.z, wa.z, acc0);
-          acc0 = fmaf(pa.w, wa.w, acc0);
+          acc1 = fmaf(pa.w, wa.w, acc1);
         }
         if (d.x & (1u << 14)) orow[d.x >> 16] = __logf(fmaxf(acc0 + acc1, kEps));  // kaldi_signal.py:540
       }
@@ -361,32 +426,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
     __syncthreads();
 
     // ---- 5. store rows + per-utterance column sums ---------------------------------------------------
-    for (int r = w; r < nrows; r += kTcWarps) {
+    for (int r = w; r < nrows && w < kTcWarps; r += kTcWarps) {
       float* dst = p.feats + ((size_t)r_b[r] * T + r_t[r]) * D_out;
       const float* src = out_stage + r * L.op;
       for (int cc = lane; cc < D_out; cc += 32) dst[cc] = src[cc];
     }
-    if ((p.utt_stats != nullptr || p.global_stats != nullptr) && tid < D_out) {
-      double s1 = 0.0, s2 = 0.0;
-      int cur_b = r_b[0];
-      for (int r = 0; r <= nrows; ++r) {
-        const int b = r < nrows ? r_b[r] : -1;
-        if (b != cur_b) {
-          if (p.utt_stats) {
-            atomicAdd(p.utt_stats + ((size_t)cur_b * 2 + 0) * D_out + tid, s1);
-            atomicAdd(p.utt_stats + ((size_t)cur_b * 2 + 1) * D_out + tid, s2);
+    if ((p.utt_stats != nullptr || p.global_stats != nullptr) && tid < 4 * D_out) {
+      const int col = tid % D_out, q = tid / D_out;  // column, 32-row group
+      const int rbeg = 32 * q, rend = min(32 * q + 32, nrows);
+      if (rbeg < rend) {
+        double s1 = 0.0, s2 = 0.0;
+        int cur_b = r_b[rbeg];
+        for (int r = rbeg; r <= rend; ++r) {
+          const int b = r < rend ? r_b[r] : -1;
+          if (b != cur_b) {
+            if (p.utt_stats) {
+              atomicAdd(p.utt_stats + ((size_t)cur_b * 2 + 0) * D_out + col, s1);
+              atomicAdd(p.utt_stats + ((size_t)cur_b * 2 + 1) * D_out + col, s2);
+            }
+            if (p.global_stats) {
+              atomicAdd(p.global_stats + col, s1);
+              atomicAdd(p.global_stats + D_out + col, s2);
+            }
+            s1 = s2 = 0.0;
+            cur_b = b;
           }
-          if (p.global_stats) {
-            atomicAdd(p.global_stats + tid, s1);
-            atomicAdd(p.global_stats + D_out + tid, s2);
+          if (r < rend) {
+            const double v = (double)out_stage[r * L.op + col];
+            s1 += v;
+            s2 = fma(v, v, s2);
           }
-          s1 = s2 = 0.0;
-          cur_b = b;
-        }
-        if (r < nrows) {
-          const double v = (double)out_stage[r * L.op + tid];
-          s1 += v;
-          s2 = fma(v, v, s2);
         }
       }
     }
