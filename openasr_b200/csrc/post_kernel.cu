@@ -13,11 +13,14 @@
 
 namespace spl {
 
-constexpr int kPostRows = 32;  // rows of one utterance per CTA
+constexpr int kPostRows = 64;  // rows of one utterance per CTA
 constexpr int kPostThreads = 256;
 
+template <bool VEC4>
 __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) {
-  __shared__ float s_mean[kMaxDm], s_istd[kMaxDm], s_tm[kMaxDm];
+  __shared__ __align__(16) float s_mean[kMaxDm];
+  __shared__ __align__(16) float s_istd[kMaxDm];
+  __shared__ __align__(16) float s_tm[kMaxDm];
   __shared__ int s_mask[2 * kMaxMasks];
   const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -25,8 +28,16 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
   const int len = (int)p.feat_len[b];
   const int nmask = p.mask_params ? (p.n_freq + p.n_time) : 0;
 
+  // rows this CTA has to touch: valid rows, plus padding rows hit by a (spilled) time mask
+  int t_hi = len;
+  for (int j = p.n_freq; j < nmask; ++j) {
+    const int e = p.mask_params[((size_t)b * nmask + j) * 2 + 1];
+    t_hi = e > t_hi ? e : t_hi;
+  }
+  if (t0 >= t_hi) return;
+
   for (int d = tid; d < Dm; d += kPostThreads) {
-    float mean = 0.f, istd = 1.f, tm = 0.f;
+    float mean = 0.f, istd = 1.f;
     double s1 = 0.0, s2 = 0.0;
     if (p.utt_stats) {
       s1 = p.utt_stats[((size_t)b * 2 + 0) * Dm + d];
@@ -38,56 +49,98 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
       double var = s2 * inv_len - umean * umean;
       var = var < 1e-20 ? 1e-20 : var;
       mean = (float)umean;
-      istd = p.norm_vars ? (float)(1.0 / sqrt(var)) : 1.f;
+      istd = p.norm_vars ? (float)rsqrt(var) : 1.f;
     } else if (p.cmvn_mode == SPL_CMVN_GLOBAL) {
       mean = p.global_mean[d];
       istd = p.norm_vars ? p.global_istd[d] : 1.f;
     }
-    // time mean of the normalised features: (sum_t x / len - mean) * istd
-    tm = (float)((umean - (double)mean) * (double)istd);
     s_mean[d] = mean;
     s_istd[d] = istd;
-    s_tm[d] = tm;
+    s_tm[d] = (float)((umean - (double)mean) * (double)istd);  // time mean of the normalised features
   }
-  for (int i = tid; i < 2 * nmask; i += kPostThreads)
-    s_mask[i] = p.mask_params[(size_t)b * 2 * nmask + i];
+  for (int i = tid; i < 2 * nmask; i += kPostThreads) s_mask[i] = p.mask_params[(size_t)b * 2 * nmask + i];
   __syncthreads();
 
-  const int tend = min(t0 + kPostRows, p.T);
+  const int tend = min(min(t0 + kPostRows, p.T), t_hi);
+  const float inv_d = 1.0f / (float)Dm;
   for (int t = t0 + w; t < tend; t += kPostThreads / 32) {
     float* row = p.feats + ((size_t)b * p.T + t) * Dm;
     bool tmask = false;
     for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
-    if (tmask) {  // may legitimately touch padding rows (reference quirk for len < width)
-      for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
-      continue;
-    }
-    if (t >= len) continue;  // padding: stays exactly 0 (freq means of a zero row are 0)
-    float y[kMaxDm / 32];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxDm / 32; ++i) {
-      const int d = lane + 32 * i;
-      y[i] = 0.f;
-      if (d < Dm) {
-        y[i] = (row[d] - s_mean[d]) * s_istd[d];
-        sum += y[i];
+    if (VEC4) {
+      // Dm % 4 == 0, rows 16-byte aligned: lane handles float4 groups lane, lane + 32 (Dm <= 256)
+      float4* row4 = reinterpret_cast<float4*>(row);
+      const int q = Dm >> 2;
+      if (tmask) {  // may legitimately touch padding rows (reference quirk for len < width)
+        for (int g = lane; g < q; g += 32) row4[g] = reinterpret_cast<const float4*>(s_tm)[g];
+        continue;
       }
-    }
-    float fm = 0.f;
-    if (p.n_freq > 0 && nmask > 0) {
+      if (t >= len) continue;  // padding: stays exactly 0 (freq means of a zero row are 0)
+      float4 y[2];
+      float sum = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      fm = sum / (float)Dm;
-    }
+      for (int i = 0; i < 2; ++i) {
+        const int g = lane + 32 * i;
+        y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < q) {
+          const float4 x = row4[g], m = reinterpret_cast<const float4*>(s_mean)[g],
+                       s = reinterpret_cast<const float4*>(s_istd)[g];
+          y[i] = make_float4((x.x - m.x) * s.x, (x.y - m.y) * s.y, (x.z - m.z) * s.z, (x.w - m.w) * s.w);
+          sum += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+        }
+      }
+      float fm = 0.f;
+      if (p.n_freq > 0 && nmask > 0) {
 #pragma unroll
-    for (int i = 0; i < kMaxDm / 32; ++i) {
-      const int d = lane + 32 * i;
-      if (d < Dm) {
-        float v = y[i];
-        for (int j = 0; j < p.n_freq && j < nmask; ++j)
-          if (d >= s_mask[2 * j] && d < s_mask[2 * j + 1]) v = fm;
-        row[d] = v;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        fm = sum * inv_d;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int g = lane + 32 * i;
+        if (g < q) {
+          float v[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+          for (int j = 0; j < p.n_freq && j < nmask; ++j) {
+            const int f0 = s_mask[2 * j], f1 = s_mask[2 * j + 1];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * g + e >= f0 && 4 * g + e < f1) v[e] = fm;
+          }
+          row4[g] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    } else {
+      if (tmask) {
+        for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
+        continue;
+      }
+      if (t >= len) continue;
+      float y[kMaxDm / 32];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxDm / 32; ++i) {
+        const int d = lane + 32 * i;
+        y[i] = 0.f;
+        if (d < Dm) {
+          y[i] = (row[d] - s_mean[d]) * s_istd[d];
+          sum += y[i];
+        }
+      }
+      float fm = 0.f;
+      if (p.n_freq > 0 && nmask > 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        fm = sum * inv_d;
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxDm / 32; ++i) {
+        const int d = lane + 32 * i;
+        if (d < Dm) {
+          float v = y[i];
+          for (int j = 0; j < p.n_freq && j < nmask; ++j)
+            if (d >= s_mask[2 * j] && d < s_mask[2 * j + 1]) v = fm;
+          row[d] = v;
+        }
       }
     }
   }
@@ -95,7 +148,11 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
 
 cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
   dim3 grid((p.T + kPostRows - 1) / kPostRows, p.B);
-  post_kernel<<<grid, kPostThreads, 0, st>>>(p);
+  const bool vec = (p.Dm & 3) == 0 && p.Dm <= 256 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
+  if (vec)
+    post_kernel<true><<<grid, kPostThreads, 0, st>>>(p);
+  else
+    post_kernel<false><<<grid, kPostThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -107,15 +164,15 @@ __global__ void __launch_bounds__(256) column_stats_kernel(const float* __restri
   const int len = (int)feat_len[b];
   const int tend = min(min(t0 + kPostRows, T), len);
   for (int d = threadIdx.x; d < Dm; d += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
+    double s1 = 0.0, s2 = 0.0;
     for (int t = t0; t < tend; ++t) {
-      const float v = feats[((size_t)b * T + t) * Dm + d];
+      const double v = (double)feats[((size_t)b * T + t) * Dm + d];
       s1 += v;
-      s2 = fmaf(v, v, s2);
+      s2 = fma(v, v, s2);
     }
     if (tend > t0) {
-      atomicAdd(utt_stats + ((size_t)b * 2 + 0) * Dm + d, (double)s1);
-      atomicAdd(utt_stats + ((size_t)b * 2 + 1) * Dm + d, (double)s2);
+      atomicAdd(utt_stats + ((size_t)b * 2 + 0) * Dm + d, s1);
+      atomicAdd(utt_stats + ((size_t)b * 2 + 1) * Dm + d, s2);
     }
   }
 }

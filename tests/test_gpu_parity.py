@@ -361,3 +361,33 @@ def test_global_cmvn_single_gpu(wavs):
     ref, _ = fo.splayer_forward(x, lens, conf, global_stats=st)
     close(feats, ref, scale=(istd.cpu().float().clamp_min(1.0))[None, None, :])
     assert len(layer.state_dict()) == 0
+
+
+def test_concurrent_host_threads_same_device(wavs):
+    """DataParallel calls the module from one Python thread per GPU (train.py:134); here several
+    threads share ONE device and one cached handle, each on its own stream: results must be identical
+    to the serial ones."""
+    import threading
+    layer, conf = make_layer(cmvn="utterance")
+    layer.eval()
+    batches = []
+    for s in range(4):
+        x, lens = fo.synth_batch(5, 8000, 60000, 16000, seed=40 + s)
+        batches.append((x.cuda(), lens))
+    serial = [layer(x, l)[0].clone() for x, l in batches]
+    out = [None] * 4
+
+    def work(i):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(10):
+                out[i] = layer(batches[i][0], batches[i][1])[0]
+        st.synchronize()
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for a, b in zip(serial, out):
+        assert torch.equal(a, b)
