@@ -325,6 +325,7 @@ def run_ours(args):
 
     # ---- e2e through SPLayer.forward with host buffers (every rank; max over ranks) ----
     e2e = run_e2e(layer, items, dev, max(8, min(K, args.e2e_steps)), world)
+    e2e_i16 = run_e2e(layer, items, dev, max(8, min(K, args.e2e_steps)), world, int16=True)
 
     if world > 1:
         dist.barrier()
@@ -341,7 +342,7 @@ def run_ours(args):
                    "dither": args.dither, "dither_rng": "device", "training": True,
                    "pool_batches": len(items), "pool_bytes": pool_bytes, "l2_flush": "pool larger than L2 (126 MB)",
                    "cuda_graph_chunk": args.graph_chunk, "batches_in_flight": args.streams, "timing": "best of %d regions of K steps, CUDA events" % args.repeats, "partition": "by utterance, %d rank(s), no data-path collective" % world},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_int16_ingest": e2e_i16,
         "gpu_launches": lps * K, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -349,7 +350,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(layer, items, dev, steps, world):
+def run_e2e(layer, items, dev, steps, world, int16=False):
     """SPLayer.forward from pinned host buffers: H2D of the fp32 wav batch, forward (host RNG draws,
     lengths/mask uploads, both kernels), D2H of the features; 3 slots in flight on 3 streams."""
     import torch.distributed as dist
@@ -359,11 +360,11 @@ def run_e2e(layer, items, dev, steps, world):
     maxT = max(it["T"] for it in items)
     B = items[0]["wav_host"].shape[0]
     d_out = items[0]["feats"].shape[2]
-    pin_in = [it["wav_host"].pin_memory() for it in items]
+    pin_in = [(it["wav_host"].to(torch.int16) if int16 else it["wav_host"]).pin_memory() for it in items]
     pin_out = [torch.empty((B * maxT * d_out,), dtype=torch.float32).pin_memory() for _ in range(nslot)]
     pin_len = [torch.empty((B,), dtype=torch.int64).pin_memory() for _ in range(nslot)]
     done = [None] * nslot
-    h2d = sum(p.numel() * 4 for p in pin_in) / len(pin_in) + 8 * B
+    h2d = sum(p.numel() * p.element_size() for p in pin_in) / len(pin_in) + 8 * B
     d2h = sum(it["feats"].numel() * 4 for it in items) / len(items) + 8 * B
 
     def one(i):
@@ -399,7 +400,8 @@ def run_e2e(layer, items, dev, steps, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         audio = float(t.item())
     return {"value": audio / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "api": "SPLayer.forward(pinned fp32 wav -> cuda, host lengths) + D2H of feats"}
+            "steps": steps, "api": "SPLayer.forward(pinned %s wav -> cuda, host lengths) + D2H of feats"
+                                   % ("int16 PCM" if int16 else "fp32")}
 
 
 def run_cpu_baseline(conf, items, sr):
