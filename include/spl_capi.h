@@ -123,6 +123,12 @@ SPL_API int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream
 SPL_API int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len, int32_t B, int32_t T,
                      int32_t Dm, double* utt_stats, void* stream);
 
+/* Host-side helper (no device work): turn the 2*(F+T) x B uniforms drawn in the reference's order
+ * (sp_layers.py:58-71) into [B, F+T, 2] half-open mask rectangles with the reference's float32
+ * arithmetic and Python slice semantics.  `frames` = valid frames per utterance (host). */
+SPL_API int spl_specaug_rects(const float* uniforms, const int64_t* frames, int32_t B, int32_t T, int32_t V,
+                              int32_t n_freq, float freq_width, int32_t n_time, float time_width, int32_t* out);
+
 /* tcgen05 building-block self-test: D[128,N] = A[128,K] * B[N,K]^T in kind::tf32 (operands are used
  * as TF32, i.e. the low 13 mantissa bits are ignored), accumulator in TMEM.  Device pointers;
  * *status (device int) becomes non-zero if the MMA completion barrier timed out. */

@@ -69,7 +69,7 @@ class SplPostArgs(C.Structure):
 
 
 EXPORTS = ("spl_create", "spl_destroy", "spl_fbank_forward", "spl_post_inplace", "spl_column_stats",
-           "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest")
+           "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest", "spl_specaug_rects")
 
 _lib = None
 
@@ -98,6 +98,9 @@ def load() -> C.CDLL:
     lib.spl_column_stats.restype = C.c_int
     lib.spl_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.spl_tc_selftest.restype = C.c_int
+    lib.spl_specaug_rects.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_int32, C.c_float, C.c_void_p]
+    lib.spl_specaug_rects.restype = C.c_int
     lib.spl_feature_dim.argtypes = [C.c_void_p]
     lib.spl_feature_dim.restype = C.c_int
     lib.spl_abi_version.argtypes = []

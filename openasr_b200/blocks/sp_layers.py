@@ -184,16 +184,17 @@ class SPLayer(nn.Module):
         # ---- fast path: one pinned upload (lengths + mask rectangles), two kernel launches ----
         dev = wav_batch.device
         h = self._handle(dev)
-        lens = self._host_lengths(lengths)
+        if isinstance(lengths, torch.Tensor):
+            lens_np = lengths.detach().cpu().numpy().astype(np.int64, copy=False)  # one D2H sync if on the GPU
+        else:
+            lens_np = np.asarray(lengths, dtype=np.int64)
         B = wav_batch.shape[0]
-        if len(lens) != B:
+        if lens_np.shape != (B,):
             raise ValueError("lengths must have one entry per utterance")
-        width = wav_batch.shape[1]
-        for n in lens:
-            assert 2 <= h.win <= n, "choose a window size %d that is [2, %d]" % (h.win, n)  # kaldi_signal.py:154
-            if n > width:
-                raise ValueError("length %d exceeds the padded batch width %d" % (n, width))
-        lens_np = np.asarray(lens, dtype=np.int64)
+        n_min = int(lens_np.min())
+        assert 2 <= h.win <= n_min, "choose a window size %d that is [2, %d]" % (h.win, n_min)  # kaldi_signal.py:154
+        if int(lens_np.max()) > wav_batch.shape[1]:
+            raise ValueError("length %d exceeds the padded batch width %d" % (int(lens_np.max()), wav_batch.shape[1]))
         frames_np = 1 + (lens_np - h.win) // h.shift
         T = int(frames_np.max())
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self._dither != 0.0 else 0
@@ -203,7 +204,7 @@ class SPLayer(nn.Module):
             conf = self.spec_aug_conf
             nf, nt = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
             u = frontend.specaug_uniforms(B, nf, nt, None).numpy()
-            arrays.append(frontend.specaug_rectangles_np(u, frames_np, T, h.d_out, conf))
+            arrays.append(frontend.specaug_rectangles_c(u, frames_np, T, h.d_out, conf))
         keep, ptrs = self._stager.upload(arrays, dev)
         utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
         feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)

@@ -524,6 +524,34 @@ int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len,
   return SPL_OK;
 }
 
+// Host helper: SpecAug rectangles from the uniforms, same float32 arithmetic and truncation as
+// sp_layers.py:59-62 / :68-71 and Python slice semantics of x[b, s:s+w] (:64, :73).
+int spl_specaug_rects(const float* uniforms, const int64_t* frames, int32_t B, int32_t T, int32_t V, int32_t n_freq,
+                      float freq_width, int32_t n_time, float time_width, int32_t* out) {
+  if (!uniforms || !frames || !out || B < 1 || n_freq < 0 || n_time < 0)
+    return fail(SPL_ERR_INVALID_ARG, "spl_specaug_rects: bad argument");
+  const int M = n_freq + n_time;
+  for (int j = 0; j < M; ++j) {
+    const float* uw = uniforms + (size_t)(2 * j) * B;
+    const float* us = uw + B;
+    const bool is_f = j < n_freq;
+    const float wmax = is_f ? freq_width : time_width;
+    const int64_t size = is_f ? V : T;
+    for (int b = 0; b < B; ++b) {
+      const int64_t width = (int64_t)(wmax * uw[b]);                              // (W * rand).long()
+      const int64_t limit = is_f ? (int64_t)V : frames[b];
+      const int64_t start = (int64_t)((float)(limit - width) * us[b]);            // ((V - fs).float() * rand).long()
+      const int64_t end = start + width;
+      int64_t s_ = start < 0 ? start + size : start, e_ = end < 0 ? end + size : end;
+      s_ = s_ < 0 ? 0 : (s_ > size ? size : s_);
+      e_ = e_ < 0 ? 0 : (e_ > size ? size : e_);
+      out[((size_t)b * M + j) * 2 + 0] = (int32_t)s_;
+      out[((size_t)b * M + j) * 2 + 1] = (int32_t)(e_ > s_ ? e_ : s_);
+    }
+  }
+  return SPL_OK;
+}
+
 int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t* status, void* stream) {
   if (!A || !B || !D || !status) return fail(SPL_ERR_INVALID_ARG, "spl_tc_selftest: null argument");
   if (N < 16 || N > 256 || (N & 15) || K < 8 || (K & 7) || (size_t)K * (128 + N) * 4 > 200 * 1024)

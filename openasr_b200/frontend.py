@@ -208,30 +208,43 @@ def specaug_rectangles(uniforms: torch.Tensor, feat_len: torch.Tensor, T: int, V
 # ---------------------------------------------------------------------- fast host path
 def specaug_rectangles_np(uniforms: np.ndarray, frames: np.ndarray, T: int, V: int, conf: dict) -> np.ndarray:
     """numpy twin of :func:`specaug_rectangles` for the per-call host path (same float32 arithmetic,
-    same truncation, same slice resolution; ~20x less dispatch overhead than tiny torch ops)."""
+    same truncation, same slice resolution), vectorised over the masks: ~15 numpy calls per forward."""
     F_, T_ = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
     B = uniforms.shape[1]
+    M = F_ + T_
+    u_w = uniforms[0::2]                      # [M, B] width draws  (fs, ts)
+    u_s = uniforms[1::2]                      # [M, B] start draws  (f0s, t0s)
+    wmax = np.empty((M, 1), dtype=np.float32)
+    wmax[:F_] = np.float32(conf["freq_mask_width"])
+    wmax[F_:] = np.float32(conf["time_mask_width"])
+    width = (wmax * u_w).astype(np.int64)                        # (W * rand).long()
+    limit = np.empty((M, B), dtype=np.int64)
+    limit[:F_] = V
+    limit[F_:] = frames.astype(np.int64)[None, :]
+    start = ((limit - width).astype(np.float32) * u_s).astype(np.int64)   # ((V - fs).float() * rand).long()
+    size = np.empty((M, 1), dtype=np.int64)
+    size[:F_] = V
+    size[F_:] = T
+    end = start + width
+    s_ = np.clip(np.where(start < 0, start + size, start), 0, size)      # Python slice semantics
+    e_ = np.clip(np.where(end < 0, end + size, end), 0, size)
+    out = np.empty((B, M, 2), dtype=np.int32)
+    out[:, :, 0] = s_.T
+    out[:, :, 1] = np.maximum(s_, e_).T
+    return out
+
+
+def specaug_rectangles_c(uniforms: np.ndarray, frames: np.ndarray, T: int, V: int, conf: dict) -> np.ndarray:
+    """Same as :func:`specaug_rectangles_np`, computed by the library's host helper (one ctypes call)."""
+    lib = _capi.load()
+    F_, T_ = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
+    B = uniforms.shape[1]
+    u = np.ascontiguousarray(uniforms, dtype=np.float32)
+    fr = np.ascontiguousarray(frames, dtype=np.int64)
     out = np.empty((B, F_ + T_, 2), dtype=np.int32)
-    flen = frames.astype(np.int64)
-
-    def resolve(start, width, size, j):
-        end = start + width
-        s_ = np.clip(np.where(start < 0, start + size, start), 0, size)
-        e_ = np.clip(np.where(end < 0, end + size, end), 0, size)
-        out[:, j, 0] = s_
-        out[:, j, 1] = np.maximum(s_, e_)
-
-    r = 0
-    for j in range(F_):
-        fs = (np.float32(conf["freq_mask_width"]) * uniforms[r]).astype(np.int64)
-        f0s = ((V - fs).astype(np.float32) * uniforms[r + 1]).astype(np.int64)
-        r += 2
-        resolve(f0s, fs, V, j)
-    for j in range(T_):
-        ts = (np.float32(conf["time_mask_width"]) * uniforms[r]).astype(np.int64)
-        t0s = ((flen - ts).astype(np.float32) * uniforms[r + 1]).astype(np.int64)
-        r += 2
-        resolve(t0s, ts, T, F_ + j)
+    _capi.check(lib.spl_specaug_rects(u.ctypes.data, fr.ctypes.data, B, int(T), int(V), F_,
+                                      float(conf["freq_mask_width"]), T_, float(conf["time_mask_width"]),
+                                      out.ctypes.data), "spl_specaug_rects")
     return out
 
 
@@ -269,8 +282,8 @@ class HostStager:
             o += sz
         dev = torch.empty(total, dtype=torch.uint8, device=device)
         dev.copy_(self._slots[i][:total], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
-        self._events[i] = ev
+        if self._events[i] is None:
+            self._events[i] = torch.cuda.Event()
+        self._events[i].record(torch.cuda.current_stream(device))
         base = dev.data_ptr()
         return dev, [base + x for x in offs]

@@ -96,6 +96,7 @@ def test_numpy_rectangles_equal_torch_rectangles():
             a = frontend.specaug_rectangles(u, lens, 500, 80, conf)
             b = frontend.specaug_rectangles_np(u.numpy(), lens.numpy(), 500, 80, conf)
             assert np.array_equal(a.numpy(), b)
+            assert np.array_equal(b, frontend.specaug_rectangles_c(u.numpy(), lens.numpy(), 500, 80, conf))
 
 
 def test_specaug_uniform_stream_equals_sequential_draws():
