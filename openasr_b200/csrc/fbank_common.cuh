@@ -45,6 +45,15 @@ __device__ __forceinline__ float dither_from_bits(uint32_t r) {
   return sqrtf(-2.0f * __logf(x)) * __cosf(6.283185307179586f * x);
 }
 
+// lg2 / ln of a NORMAL positive float on the MUFU pipe (flush-to-zero form: no denormal pre-scaling code;
+// every argument here is >= 2^-23, far from the denormal range)
+__device__ __forceinline__ float fast_log2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_log(float x) { return fast_log2(x) * 0.6931471805599453f; }
+
 __device__ __forceinline__ float group_sum(float v, int width) {
   // butterfly reduction inside aligned groups of `width` lanes (16 or 32)
   if (width == 32) v += __shfl_xor_sync(0xffffffffu, v, 16);

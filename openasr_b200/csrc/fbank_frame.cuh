@@ -61,8 +61,10 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint32_t k0, uint32_t k
 __device__ __forceinline__ float dither_term(uint32_t v24, float d2) {
   const float v = (float)max(v24, 2u);
   // -2 ln(v 2^-24) = (24 - lg2 v) * 2 ln 2
-  const float a = fmaf(__log2f(v), -1.3862943611198906f * d2, 33.27106466687737f * d2);
-  return fast_sqrt(a) * __cosf(v * 3.7450703370559213e-07f);  // 2 pi 2^-24
+  const float a = fmaf(fast_log2(v), -1.3862943611198906f * d2, 33.27106466687737f * d2);
+  float cs;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(v * 3.7450703370559213e-07f));  // 2 pi 2^-24
+  return fast_sqrt(a) * cs;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -138,7 +140,7 @@ __device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& 
       e = fmaf(d, d, e);
     }
     e = group_sum(e, G::R2);
-    if (n2 == 0) *energy_slot = __logf(fmaxf(e, kEps));
+    if (n2 == 0) *energy_slot = fast_log(fmaxf(e, kEps));
   }
   const float c = p.preemph;
   const float mu = (1.0f - c) * mean;

@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_persistent_kernel(const Fba
           accA = fmaf(pa.w, wa.w, accA);
           accB = fmaf(pb.w, wb.w, accB);
         }
-        orow[2 * i] = __logf(fmaxf(accA, kEps));  // kaldi_signal.py:540
-        if (dsc >> 31) orow[2 * i + 1] = __logf(fmaxf(accB, kEps));
+        orow[2 * i] = fast_log(fmaxf(accA, kEps));  // kaldi_signal.py:540
+        if (dsc >> 31) orow[2 * i + 1] = fast_log(fmaxf(accB, kEps));
       }
       if (p.use_energy && w == 0 && hsel == 0) orow[-1] = energy[fr];
     }

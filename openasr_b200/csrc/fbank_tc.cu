@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
         if (lane == 0) {
           const float mu = (1.0f - c) * mean;
           r_mu[r] = mu;
-          r_en[r] = __logf(fmaxf(e, kEps));
+          r_en[r] = fast_log(fmaxf(e, kEps));
           r_sg[r] = 0.f;
           r_zh[r] = NB < Nw ? win[NB] * (xh - c * xhm - mu) : 0.f;
         }
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fbank_tc_kernel(const FbankPara
           acc0 = fmaf(pa.z, wa.z, acc0);
           acc1 = fmaf(pa.w, wa.w, acc1);
         }
-        if (d.x & (1u << 14)) orow[d.x >> 16] = __logf(fmaxf(acc0 + acc1, kEps));  // kaldi_signal.py:540
+        if (d.x & (1u << 14)) orow[d.x >> 16] = fast_log(fmaxf(acc0 + acc1, kEps));  // kaldi_signal.py:540
       }
       if (p.use_energy && cg == 0) out_stage[row * L.op] = r_en[row];
     }

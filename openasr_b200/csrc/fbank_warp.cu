@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
           accB = fmaf(pb.w, wb.w, accB);
         }
         const int m0 = 2 * (8 * j + sl);
-        if (dsc & 0x40000000u) orow[m0] = __logf(fmaxf(accA, kEps));  // kaldi_signal.py:540
-        if (dsc & 0x80000000u) orow[m0 + 1] = __logf(fmaxf(accB, kEps));
+        if (dsc & 0x40000000u) orow[m0] = fast_log(fmaxf(accA, kEps));  // kaldi_signal.py:540
+        if (dsc & 0x80000000u) orow[m0 + 1] = fast_log(fmaxf(accB, kEps));
       }
       if (p.use_energy && lane < 4) orows[lane * OP] = energy[lane];
     }
