@@ -144,14 +144,17 @@ __device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& 
   }
   const float c = p.preemph;
   const float mu = (1.0f - c) * mean;
+  [[maybe_unused]] float rot_prev = 0.f;  // NOISE: row n1 - 1 rotated by one lane (lane 0 <- lane R2 - 1)
 #pragma unroll
   for (int n1 = 0; n1 < F::NROW; ++n1) {
     float prev;
-    if constexpr (NOISE) {  // previous sample of the noisy frame lives in the neighbouring lane
-      const float up = __shfl_up_sync(0xffffffffu, x[n1], 1, G::R2);
-      float wrap = x[0];  // j == 0: replicate padding (kaldi_signal.py:192-193)
-      if (n1 > 0) wrap = __shfl_sync(0xffffffffu, x[n1 - 1], G::R2 - 1, G::R2);
-      prev = (n2 == 0) ? wrap : up;
+    if constexpr (NOISE) {
+      // previous sample of the noisy frame: the neighbouring lane's x[n1], and for lane 0 the last
+      // lane's x[n1 - 1] -- which is what lane 0 received from the previous row's rotation
+      const float rot = __shfl_sync(0xffffffffu, x[n1], (n2 + G::R2 - 1) & (G::R2 - 1), G::R2);
+      const float wrap = n1 == 0 ? x[0] : rot_prev;  // j == 0: replicate padding (kaldi_signal.py:192-193)
+      prev = (n2 == 0) ? wrap : rot;
+      rot_prev = rot;
     } else {
       const int j = G::R2 * n1 + n2;
       prev = (n1 == 0 && n2 == 0) ? x[0] : fr[(row_valid<NFFT, NW>(n1, n2, Nw) ? j : 1) - 1];

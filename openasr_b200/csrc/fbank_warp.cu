@@ -18,9 +18,23 @@
 
 namespace spl {
 
+#ifdef SPL_TRACE  // per-warp clock64 timeline (tools/trace_warp.py); never defined in the shipped library
+__device__ unsigned long long g_trace[296 * 8 * 32];
+#define TR(slot)                                                                                   \
+  do {                                                                                             \
+    if (lane == 0 && (slot) < 32) g_trace[((size_t)blockIdx.x * 8 + w) * 32 + (slot)] = clock64(); \
+  } while (0)
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#else
+#define TR(slot) do { } while (0)
+#endif
+
 constexpr int kWWarps = 8;   // two such CTAs per SM: 16 resident warps (register-file bound at 128 regs)
 constexpr int kWThreads = kWWarps * 32;
-constexpr int kStatUtts = 4;  // utterances a CTA can merge in shared memory (more: direct global atomics)
 
 struct WLayout {
   int pair;      // floats of one pair's exchange area (re plane + im plane)
@@ -30,7 +44,7 @@ struct WLayout {
   int en_off;    // 4 energy slots
   int st_off;    // this warp's running column sums of the current utterance: [2][op]
   int rw;        // region stride (multiple of 4)
-  int off_tab, off_gpre, off_fpre, off_stat, off_ctl, off_bar, off_warp, total;
+  int off_tab, off_gpre, off_fpre, off_ctl, off_bar, off_warp, total;
 };
 
 __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words) {
@@ -47,9 +61,8 @@ __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_o
   L.off_tab = 0;
   L.off_gpre = wtab_words;
   L.off_fpre = L.off_gpre + kMaxPersistentB + 1;
-  L.off_stat = (L.off_fpre + kMaxPersistentB + 1 + 3) & ~3;
-  L.off_ctl = L.off_stat + kStatUtts * 4 * L.op;  // fp64 [kStatUtts][2][op]
-  L.off_bar = (L.off_ctl + 8 + 1) & ~1;
+  L.off_ctl = (L.off_fpre + kMaxPersistentB + 1 + 3) & ~3;
+  L.off_bar = (L.off_ctl + 8 + kWWarps + 1) & ~1;  // ctl[8] + last utterance of every warp
   L.off_warp = (L.off_bar + 2 * (kWWarps + 1) + 31) & ~31;
   L.total = L.off_warp + kWWarps * L.rw;
   (void)S;
@@ -78,12 +91,16 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   const float* tws = tab + p.tab.wt_off_tw;
   int* gpre = reinterpret_cast<int*>(smem + L.off_gpre);  // gpre[b] = groups of utterances < b
   int* fpre = reinterpret_cast<int*>(smem + L.off_fpre);  // fpre[b] = frames of utterances < b
-  double* cstat = reinterpret_cast<double*>(smem + L.off_stat);  // [kStatUtts][2][op]
-  int* ctl = reinterpret_cast<int*>(smem + L.off_ctl);    // [0] next group
+  int* ctl = reinterpret_cast<int*>(smem + L.off_ctl);    // [0] next group ... [8 + w] last utterance of warp w
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [0] tables, [1 + w] samples of warp w
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int B = p.B, T = p.T, OP = L.op;
+  TR(0);
+#ifdef SPL_TRACE
+  if (lane == 0) g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 1] = gtimer();
+  int tr_it = 0;
+#endif
   float* wr = smem + L.off_warp + w * L.rw;  // this warp's region
   float* e0 = wr;                            // pair 0 exchange: re plane, im plane at + PL ; power rows alias it
   float* e1 = wr + L.p1;                     // pair 1 exchange ; the sample buffer aliases it
@@ -101,7 +118,6 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
     mbar_expect_tx(bars, (uint32_t)p.tab.wtab_words * 4u);
     bulk_g2s(tab, p.tab.wtab, (uint32_t)p.tab.wtab_words * 4u, bars);
   }
-  for (int i = tid; i < kStatUtts * 2 * OP; i += kWThreads) cstat[i] = 0.0;
   if (w == 0) {
     int carry = 0, fcarry = 0;
     for (int base = 0; base < B; base += 32) {
@@ -137,56 +153,42 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
     }
   }
   for (int i = lane; i < 2 * OP; i += 32) wstat[i] = 0.0;
+  TR(22);
   __syncthreads();
-  if (tid == 0) {  // this CTA's contiguous share of the group list (64-bit division once, not per thread)
-    const long long NG = gpre[B];
-    const int g0 = (int)(NG * blockIdx.x / gridDim.x), g1 = (int)(NG * (blockIdx.x + 1) / gridDim.x);
-    int lo = 0, hi = B - 1;  // utterance of the first group
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (gpre[mid] <= g0) lo = mid; else hi = mid - 1;
-    }
-    ctl[0] = g0;  // next group to hand out
-    ctl[1] = g1;
-    ctl[2] = lo;
-    // share of the B*T - frames zero-padding rows
-    const long long total_pad = (long long)B * T - fpre[B];
-    ctl[3] = (int)(total_pad * blockIdx.x / gridDim.x);
-    ctl[4] = (int)(total_pad * (blockIdx.x + 1) / gridDim.x);
-  }
-  __syncthreads();
-  const int g1 = ctl[1], b_first = ctl[2];
-
-  // ---- 0b. zero padding rows: an equal share of the padded rows per CTA (sp_layers.py:88) -------
-  {
-    int q = ctl[3];
-    const int q1 = ctl[4];
-    if (q < q1) {
-      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
+  TR(23);
+  // This CTA's contiguous share of the group list (thread 0) and of the zero-padding rows (thread 32).
+  // floor(total * i / G) = q i + floor(r i / G) with total = q G + r: 32-bit divisions only (a 64-bit
+  // division costs ~500 cycles of a single thread while the whole CTA waits).
+  if (tid == 0 || tid == 32) {
+    const unsigned G = gridDim.x, bid = blockIdx.x;
+    auto share = [&](long long total, unsigned i) -> int {
+      if (total < 0x7fffffffLL && G < 0x10000u) {
+        const unsigned t32 = (unsigned)total, q = t32 / G, r = t32 - q * G;
+        return (int)(q * i + (r * i) / G);
+      }
+      return (int)(total * i / G);
+    };
+    if (tid == 0) {
+      const int g0 = share(gpre[B], bid), g1 = share(gpre[B], bid + 1);
+      int lo = 0, hi = B - 1;  // utterance of the first group
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+        if (gpre[mid] <= g0) lo = mid; else hi = mid - 1;
       }
-      int b = lo;
-      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
-      while (q < q1) {
-        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
-        const int m_b = fpre[b + 1] - fpre[b];
-        const int ofs = q - (b * T - fpre[b]);
-        int nrows = (T - m_b) - ofs;
-        nrows = nrows > q1 - q ? q1 - q : nrows;
-        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
-        if (vec) {
-          float4* d4 = reinterpret_cast<float4*>(dst);
-          const int n4 = nrows * (D_out >> 2);
-          for (int i = tid; i < n4; i += kWThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          for (int i = tid; i < nrows * D_out; i += kWThreads) dst[i] = 0.f;
-        }
-        q += nrows;
-      }
+      ctl[0] = g0 + kWWarps;  // next group to hand out: warp w starts on group g0 + w
+      ctl[1] = g1;
+      ctl[2] = lo;
+      ctl[5] = g0;
+      ctl[6] = 0;  // valid rows this CTA contributed to the global statistics
+    } else {
+      const long long total_pad = (long long)B * T - fpre[B];
+      ctl[3] = share(total_pad, bid);
+      ctl[4] = share(total_pad, bid + 1);
     }
   }
+  __syncthreads();
+  TR(24);
+  const int g1 = ctl[1], b_first = ctl[2];
 
   // ---- per-warp helpers ---------------------------------------------------------------------------
   const char* wav_lo = static_cast<const char*>(p.wav);
@@ -231,49 +233,80 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
     }
   };
 
-  mbar_wait(bars, 0);  // tables have landed
-
-  // per-utterance column sums (CMVN / SpecAug time means): running sums of this warp's current
-  // utterance live in its own shared-memory rows and are merged into the CTA table on a change
+  // per-utterance column sums (CMVN / SpecAug time means): running fp64 sums of this warp's current
+  // utterance live in its own shared-memory rows; the CTA merges them once, after the loop
   int stat_b = -1, stat_rows = 0;
   const bool want_stats = p.utt_stats != nullptr || p.global_stats != nullptr;
-  auto flush_stats = [&]() {
+  auto flush_stats = [&]() {  // utterance change inside the loop (rare: a CTA's share spans 1-2 utterances)
     if (stat_b < 0) return;
-    const int slot = stat_b - b_first;
     for (int c = lane; c < D_out; c += 32) {
       const double v1 = wstat[c], v2 = wstat[OP + c];
       wstat[c] = 0.0;
       wstat[OP + c] = 0.0;
-      if (slot < kStatUtts) {
-        atomicAdd(cstat + (slot * 2 + 0) * OP + c, v1);
-        atomicAdd(cstat + (slot * 2 + 1) * OP + c, v2);
-      } else {
-        if (p.utt_stats) {
-          atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 0) * D_out + c, v1);
-          atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 1) * D_out + c, v2);
-        }
-        if (p.global_stats) {
-          atomicAdd(p.global_stats + c, v1);
-          atomicAdd(p.global_stats + D_out + c, v2);
-        }
+      if (p.utt_stats) {
+        atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 0) * D_out + c, v1);
+        atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 1) * D_out + c, v2);
+      }
+      if (p.global_stats) {
+        atomicAdd(p.global_stats + c, v1);
+        atomicAdd(p.global_stats + D_out + c, v2);
       }
     }
-    if (p.global_stats && lane == 0) atomicAdd(p.global_stats + 2 * D_out, (double)stat_rows);
+    if (p.global_stats && lane == 0) atomicAdd(ctl + 6, stat_rows);
     stat_rows = 0;
   };
 
   // ---- main loop: one group (<= 4 frames of one utterance) per iteration, no block-wide barriers ----
   uint32_t parity = 0;
   Grp cur, nxt;
-  int g_cur = fetch_group();
+  int g_cur = ctl[5] + w;
   if (g_cur < g1) stage_group(g_cur, cur);
+  TR(25);
+
+  // ---- zero padding rows: an equal share of the padded rows per CTA (sp_layers.py:88), written while
+  // the first group's samples are in flight ----
+  {
+    int q = ctl[3];
+    const int q1 = ctl[4];
+    if (q < q1) {
+      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+      }
+      int b = lo;
+      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
+      while (q < q1) {
+        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
+        const int m_b = fpre[b + 1] - fpre[b];
+        const int ofs = q - (b * T - fpre[b]);
+        int nrows = (T - m_b) - ofs;
+        nrows = nrows > q1 - q ? q1 - q : nrows;
+        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
+        if (vec) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const int n4 = nrows * (D_out >> 2);
+          for (int i = tid; i < n4; i += kWThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int i = tid; i < nrows * D_out; i += kWThreads) dst[i] = 0.f;
+        }
+        q += nrows;
+      }
+    }
+  }
+
+  TR(2);
+  mbar_wait(bars, 0);  // tables have landed (the first group's samples are already in flight)
+  TR(3);
   while (g_cur < g1) {
     const int g_nxt = fetch_group();
     const int n = cur.n;
     const int need = (n - 1) * S + Nw;
+    TR(4 + 6 * tr_it);
     if (cur.bulk) {
       mbar_wait(mybar, parity);
       parity ^= 1;
+      TR(5 + 6 * tr_it);
     } else {  // scalar staging (int16 ingest, unaligned or boundary windows)
       const size_t gofs = (size_t)cur.b * p.wav_pitch + (size_t)cur.t0 * S;
       if (p.sample_format == SPL_SAMPLES_F32) {
@@ -348,6 +381,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       }
     }
     __syncwarp();
+    TR(6 + 6 * tr_it);
 
     // ---- stage 2: lane = (pair, k1), registers = n2 ----
     const int pr = lane >> 4, k1 = lane & 15;
@@ -386,6 +420,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       }
     }
     __syncwarp();
+    TR(7 + 6 * tr_it);
 
     // ---- mel: lane = (frame f, slice s); iteration j handles filter pairs 8 j + s ----
     {
@@ -400,8 +435,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         const float4* pa4 = prow4 + (dsc & 63u);
         const float4* pb4 = prow4 + ((dsc >> 6) & 63u);
         float accA = 0.f, accB = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < n4; ++g) {
+        auto mac = [&](int g) {
           const float4 pa = pa4[g], pb = pb4[g];
           const float4 wa = wv[16 * g], wb = wv[16 * g + 8];
           accA = fmaf(pa.x, wa.x, accA);
@@ -412,7 +446,14 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
           accB = fmaf(pb.z, wb.z, accB);
           accA = fmaf(pa.w, wa.w, accA);
           accB = fmaf(pb.w, wb.w, accB);
+        };
+        int g = 0;
+#pragma unroll 1
+        for (; g + 2 <= n4; g += 2) {  // two 4-bin groups per trip: half the pointer / branch overhead
+          mac(g);
+          mac(g + 1);
         }
+        if (g < n4) mac(g);
         const int m0 = 2 * (8 * j + sl);
         if (dsc & 0x40000000u) orow[m0] = fast_log(fmaxf(accA, kEps));  // kaldi_signal.py:540
         if (dsc & 0x80000000u) orow[m0 + 1] = fast_log(fmaxf(accB, kEps));
@@ -420,6 +461,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       if (p.use_energy && lane < 4) orows[lane * OP] = energy[lane];
     }
     __syncwarp();
+    TR(8 + 6 * tr_it);
 
     // ---- store the group's rows (contiguous in global memory) + column sums ----
     {
@@ -452,27 +494,60 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       }
     }
     __syncwarp();  // output rows / power rows are rewritten by the next iteration
+    TR(9 + 6 * tr_it);
+#ifdef SPL_TRACE
+    ++tr_it;
+#endif
     g_cur = g_nxt;
     cur = nxt;
   }
 
-  // ---- epilogue: merge the CTA's column sums, one fp64 atomic per (utterance, column) ----
+  TR(30);
+  // ---- epilogue: the warps' running sums (one utterance each) are merged by column, without
+  // shared-memory atomics: thread i owns entry i of the [2][OP] rows and walks the 8 warps ----
   if (want_stats) {
-    flush_stats();
+    if (lane == 0) {
+      ctl[8 + w] = stat_b;
+      if (p.global_stats && stat_rows) atomicAdd(ctl + 6, stat_rows);
+    }
     __syncthreads();
-    for (int sw = 0; sw < 2 * kStatUtts; ++sw) {
-      const int slot = sw >> 1, which = sw & 1, b = b_first + slot;
-      if (b >= B) break;
-      for (int c = tid; c < D_out; c += kWThreads) {
-        const double v = cstat[sw * OP + c];
-        if (v != 0.0) {
+    int b_lo = 0x7fffffff, b_hi = -1;
+#pragma unroll
+    for (int ww = 0; ww < kWWarps; ++ww) {
+      const int bw = ctl[8 + ww];
+      if (bw >= 0) {
+        b_lo = bw < b_lo ? bw : b_lo;
+        b_hi = bw > b_hi ? bw : b_hi;
+      }
+    }
+    for (int i = tid; i < 2 * OP; i += kWThreads) {
+      const int which = i >= OP ? 1 : 0, c = i - which * OP;
+      if (c >= D_out) continue;
+      for (int b = b_lo; b <= b_hi; ++b) {
+        double v = 0.0;
+        bool any = false;
+#pragma unroll
+        for (int ww = 0; ww < kWWarps; ++ww)
+          if (ctl[8 + ww] == b) {
+            v += reinterpret_cast<const double*>(smem + L.off_warp + ww * L.rw + L.st_off)[i];
+            any = true;
+          }
+        if (any) {
           if (p.utt_stats) atomicAdd(p.utt_stats + ((size_t)b * 2 + which) * D_out + c, v);
           if (p.global_stats) atomicAdd(p.global_stats + which * D_out + c, v);
         }
       }
     }
+    if (p.global_stats && tid == 0 && ctl[6]) atomicAdd(p.global_stats + 2 * D_out, (double)ctl[6]);
   }
+  TR(31);
 }
+
+#ifdef SPL_TRACE
+extern "C" __attribute__((visibility("default"))) int spl_debug_trace(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 template <int NFFT, int NW, bool NOISE>

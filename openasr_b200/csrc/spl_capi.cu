@@ -1,5 +1,6 @@
 // C-ABI of the B200 speech front-end: handle management, argument validation, launches.
 // See include/spl_capi.h for the contract and the reference interfaces each entry replaces.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -47,6 +48,8 @@ struct spl_handle {
   int num_sms;
   int kernel;  // 0 warp-pipelined (default), 1 simple one-tile-per-CTA (SPL_LEGACY_KERNEL=1), 2 persistent CTA tiles (=2)
   size_t smem_warp;
+  size_t smem_pair;
+  int ctas_per_sm;
   void* blob;  // single device allocation holding every table
   spl::Tables tab;
   size_t smem_bytes;
@@ -190,6 +193,55 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
       goff += n4j;
     }
   }
+  // ---- pair-pipelined kernel table block (see spl_internal.cuh / fbank_pair.cu) ----
+  std::vector<float> qw;
+  std::vector<uint32_t> qdesc;
+  int qE = 0;
+  if (nfft == 512) {
+    std::vector<int> lo4(D), n4(D), order(D);
+    for (int m = 0; m < D; ++m) {
+      lo4[m] = cnt[m] > 0 ? (lo[m] & ~3) : 0;
+      n4[m] = cnt[m] > 0 ? (lo[m] + cnt[m] - lo4[m] + 3) / 4 : 1;  // empty filters still emit log(eps)
+      if (lo4[m] + 4 * n4[m] > nb) lo4[m] = nb - 4 * n4[m];
+      order[m] = m;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n4[a] > n4[b]; });
+    std::vector<std::vector<int>> streams(32);
+    std::vector<int> load(32, 0);
+    for (int m : order) {  // longest first onto the least-loaded stream
+      int best = 0;
+      for (int s2 = 1; s2 < 32; ++s2)
+        if (load[s2] < load[best]) best = s2;
+      streams[best].push_back(m);
+      load[best] += n4[m];
+    }
+    for (int s2 = 0; s2 < 32; ++s2) qE = load[s2] > qE ? load[s2] : qE;
+    qw.assign((size_t)qE * 32 * 4, 0.f);
+    qdesc.assign((size_t)qE * 32, 0u);
+    for (int st2 = 0; st2 < 32; ++st2) {
+      const int sl = st2 & 15, t = st2 >> 4;
+      int e = 0;
+      for (int m : streams[st2])
+        for (int g = 0; g < n4[m]; ++g, ++e) {
+          for (int q = 0; q < 4; ++q) {
+            const int k = lo4[m] + 4 * g + q;
+            const bool in = k >= lo[m] && k < lo[m] + cnt[m];
+            qw[((size_t)(e * 2 + t) * 16 + sl) * 4 + q] = in ? 0.25f * mel_dense[(size_t)m * nb + k] : 0.f;
+          }
+          qdesc[((size_t)e * 16 + sl) * 2 + t] =
+              (uint32_t)(lo4[m] / 4 + g) | ((uint32_t)m << 8) | (g == n4[m] - 1 ? 0x10000u : 0u);
+        }
+    }
+  }
+  std::vector<float> qtw2(64, 0.f);
+  for (int typ = 0; typ < 2; ++typ)
+    for (int k = 0; k < 8; ++k) {
+      const double a0 = 2.0 * M_PI * (double)(typ * k) / 32.0, a1 = 2.0 * M_PI * (double)((typ + 2) * k) / 32.0;
+      qtw2[(typ * 8 + k) * 4 + 0] = (float)std::cos(a0);
+      qtw2[(typ * 8 + k) * 4 + 1] = (float)std::sin(a0);
+      qtw2[(typ * 8 + k) * 4 + 2] = (float)std::cos(a1);
+      qtw2[(typ * 8 + k) * 4 + 3] = (float)std::sin(a1);
+    }
   // ---- tcgen05 DFT-as-GEMM tables (see spl_internal.cuh / fbank_tc.cu) ----
   const int half = nfft / 4, units = nfft / 32;
   auto tf32_rn = [](double v) {  // nearest TF32 (10 explicit mantissa bits), returned as float
@@ -297,7 +349,9 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   const size_t tt_desc = pad4(sw.size()), tt_win = tt_desc + pad4(sdesc.size()), tt_wc = tt_win + pad4(Nw);
   const size_t tt_ws = tt_wc + pad4(nb), tt_words = tt_ws + pad4(nb);
   const size_t tcb_words = tcb.size();  // multiple of 4
-  const size_t n_items = pt_words + wt_words + tt_words + tcb_words + (size_t)Nw + 2 * (size_t)R2 * 16 +
+  const size_t qt_desc = pad4(qw.size()), qt_win = qt_desc + pad4(qdesc.size()), qt_tw = qt_win + pad4(Nw);
+  const size_t qt_tw2 = qt_tw + 2 * (size_t)nfft, qt_words = qt_tw2 + 64;
+  const size_t n_items = pt_words + wt_words + tt_words + tcb_words + qt_words + (size_t)Nw + 2 * (size_t)R2 * 16 +
                          (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
   std::vector<uint32_t> host(n_items, 0u);
   std::memcpy(host.data(), pw.data(), pw.size() * 4);
@@ -325,7 +379,15 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     std::memcpy(tt + tt_ws, wsn.data(), nb * 4);
     std::memcpy(tt + tt_words, tcb.data(), tcb_words * 4);
   }
-  size_t o = pt_words + wt_words + tt_words + tcb_words;
+  {
+    uint32_t* qt = host.data() + pt_words + wt_words + tt_words + tcb_words;  // all multiples of 4: 16-byte aligned
+    if (!qw.empty()) std::memcpy(qt, qw.data(), qw.size() * 4);
+    if (!qdesc.empty()) std::memcpy(qt + qt_desc, qdesc.data(), qdesc.size() * 4);
+    std::memcpy(qt + qt_win, window, Nw * 4);
+    std::memcpy(qt + qt_tw, host.data() + pt_tw, 2 * (size_t)nfft * 4);
+    std::memcpy(qt + qt_tw2, qtw2.data(), 64 * 4);
+  }
+  size_t o = pt_words + wt_words + tt_words + tcb_words + qt_words;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -383,11 +445,23 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.tc_off_ws = (int32_t)tt_ws;
   h->tab.tc_nseg = nseg;
   for (int g = 0; g < 5; ++g) h->tab.tc_sgrp_beg[g] = sgrp[g];
+  h->tab.qtab = fb + pt_words + wt_words + tt_words + tcb_words;
+  h->tab.qtab_words = (int32_t)qt_words;
+  h->tab.qt_off_desc = (int32_t)qt_desc;
+  h->tab.qt_off_win = (int32_t)qt_win;
+  h->tab.qt_off_tw = (int32_t)qt_tw;
+  h->tab.qt_off_tw2 = (int32_t)qt_tw2;
+  h->tab.qE = qE;
   for (int w = 0; w <= spl::kWarps; ++w) h->tab.pgrp_beg[w] = pgrp[w];
   h->num_sms = 148;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   const char* leg = std::getenv("SPL_LEGACY_KERNEL");
-  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '3') ? leg[0] - '0' : 0;  // 3: tcgen05 DFT-as-GEMM (experimental)
+  // 3: tcgen05 DFT-as-GEMM (experimental), 4: pair-pipelined (Nfft = 512)
+  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '4') ? leg[0] - '0' : 0;
+  const char* cps = std::getenv("SPL_CTAS_PER_SM");  // experiment knob: persistent CTAs per SM (1 or 2)
+  h->ctas_per_sm = (cps && cps[0] == '1') ? 1 : 2;
+  h->smem_pair = nfft == 512 ? spl::fbank_pair_smem_bytes(h->D_out, (int)qt_words) : 0;
+  if (h->kernel == 4 && (nfft != 512 || h->smem_pair > 113 * 1024 || S + Nw + 4 > 564)) h->kernel = 0;
   h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words);
   {  // the warp kernel stages a group's samples inside one pair's exchange planes
     const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
@@ -458,8 +532,10 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   if (h->kernel == 3 && a->B <= spl::kMaxPersistentB && a->sample_format == SPL_SAMPLES_F32 && h->cfg.dither == 0.f &&
       h->cfg.window_size * 2 > h->cfg.padded_size)
     e = spl::launch_fbank_tc(p, h->cfg.padded_size, with_noise, h->num_sms, st);
-  else if ((h->kernel == 0 || h->kernel == 3) && a->B <= spl::kMaxPersistentB)
-    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
+  else if (h->kernel == 4 && a->B <= spl::kMaxPersistentB)
+    e = spl::launch_fbank_pair(p, with_noise, h->ctas_per_sm * h->num_sms, st);
+  else if ((h->kernel == 0 || h->kernel == 3 || h->kernel == 4) && a->B <= spl::kMaxPersistentB)
+    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, h->ctas_per_sm * h->num_sms, st);
   else if (h->kernel == 2 && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
   else

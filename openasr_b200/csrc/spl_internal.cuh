@@ -56,6 +56,13 @@ struct Tables {
   int32_t tc_tab_words, tc_off_desc, tc_off_win, tc_off_wc, tc_off_ws;
   int32_t tc_nseg;
   int32_t tc_sgrp_beg[5];
+  // pair-pipelined kernel (fbank_pair.cu, Nfft = 512): mel phase with lane = (frame f = lane & 1,
+  // slice s = lane >> 1) and two filter streams t per slice; stream (s, t) walks qE flat entries.
+  //   [weights: float4 index (e * 2 + t) * 16 + s | entry descriptors: uint2 (t = 0, t = 1) at e * 16 + s,
+  //    each  bin/4 | filter << 8 | last-of-filter << 16 | window | stage-1 twiddles^T |
+  //    stage-2 twiddles: float4 {cos, sin (a = typ), cos, sin (a = typ + 2)} of 2 pi a k / 32 at typ * 8 + k]
+  const float* qtab;
+  int32_t qtab_words, qt_off_desc, qt_off_win, qt_off_tw, qt_off_tw2, qE;
 };
 
 struct FbankParams {
@@ -99,6 +106,9 @@ size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_
 // warp-pipelined kernel: one CTA of 16 independent warps per SM, no block-wide barriers in the loop
 cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
 size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words);
+// pair-pipelined kernel (Nfft = 512 only): 2 CTAs x 12 warps per SM, one packed pair per warp iteration
+cudaError_t launch_fbank_pair(const FbankParams& p, bool with_noise, int num_ctas, cudaStream_t st);
+size_t fbank_pair_smem_bytes(int D_out, int qtab_words);
 cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);

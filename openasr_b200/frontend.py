@@ -109,7 +109,7 @@ def get_handle(device: torch.device, sample_rate: float, num_mel_bins: int, use_
     """Handle cache keyed by (device, config); safe under DataParallel's per-GPU threads."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     key = (idx, float(sample_rate), int(num_mel_bins), bool(use_energy), float(dither), str(window_type),
-           os.environ.get("SPL_LEGACY_KERNEL", ""))  # the library reads the switch at spl_create
+           os.environ.get("SPL_LEGACY_KERNEL", ""), os.environ.get("SPL_CTAS_PER_SM", ""))  # the library reads the switch at spl_create
     with _handles_lock:
         h = _handles.get(key)
         if h is None:

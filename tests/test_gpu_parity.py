@@ -290,13 +290,14 @@ def test_persistent_kernel_matches_simple_kernel(monkeypatch, wavs):
     x, lens = fo.synth_batch(9, 500, 70000, 16000, seed=4)
     x = torch.cat([x, torch.zeros(9, 3)], dim=1)          # odd row pitch -> unaligned rows
     outs = {}
-    for mode in ("0", "1", "2"):  # 0 warp-pipelined (default), 1 simple one-tile-per-CTA, 2 persistent CTA tiles
+    # 0 warp-pipelined, 1 simple one-tile-per-CTA, 2 persistent CTA tiles, 4 pair-pipelined
+    for mode in ("0", "1", "2", "4"):
         monkeypatch.setenv("SPL_LEGACY_KERNEL", mode)
         layer, conf = make_layer(use_energy=True)
         layer.eval()
         xc = x.cuda()
         outs[mode] = (layer(xc, lens)[0], layer(xc[:, 1:], (lens - 1).clamp_min(400))[0])
-    for other in ("0", "2"):  # different rounding order only (fma forms): well inside the tolerance
+    for other in ("0", "2", "4"):  # different rounding order only (fma forms): well inside the tolerance
         for a, b in zip(outs[other], outs["1"]):
             assert (a - b).abs().max().item() < 2e-3 and (a - b).abs().mean().item() < 1e-5
     assert torch.equal(outs["0"][0] == 0, outs["1"][0] == 0)
