@@ -438,7 +438,7 @@ def main():
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--graph-chunk", type=int, default=64)
     ap.add_argument("--repeats", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight inside the graph")
+    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight inside the graph")
     ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

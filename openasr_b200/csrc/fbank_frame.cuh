@@ -3,6 +3,7 @@
 // (kaldi_signal.py:174-199) in the stage-1 register layout.
 #pragma once
 #include "fbank_common.cuh"
+#include "fft_c2.cuh"
 
 namespace spl {
 
@@ -166,6 +167,114 @@ __device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& 
 #pragma unroll
   for (int n1 = F::NROW; n1 < 16; ++n1) z[n1] = 0.f;
   (void)valid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two frames at once in the packed stage-1 layout: z[n1] = (frame A sample, frame B sample) of
+// j = R2 n1 + n2 after dither -> DC removal -> (raw log-energy) -> pre-emphasis -> window
+// (kaldi_signal.py:174-199).  Frame A becomes the real part and frame B the imaginary part of the
+// complex FFT input, so every arithmetic step is one fp32x2 instruction for both frames.
+template <int NFFT, int NW, bool NOISE>
+__device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& p, const float* frA, const float* frB,
+                                                const float* win, float* energy_slots /*[2]*/, int n2, int b, int tA,
+                                                int tB, bool validA, bool validB) {
+  using G = Geo<NFFT>;
+  using F = FG<NFFT, NW>;
+  const int Nw = F::kStatic ? NW : p.Nw;
+  c2 x[F::NROW];
+#pragma unroll
+  for (int n1 = 0; n1 < F::NROW; ++n1) {
+    const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
+    x[n1] = c2_make(rv ? frA[G::R2 * n1 + n2] : 0.f, rv ? frB[G::R2 * n1 + n2] : 0.f);
+  }
+  if constexpr (NOISE) {
+    if (p.noise != nullptr) {  // parity mode: host-drawn rand_gauss, [B, T, Nw]
+      const float* nzA = p.noise + ((size_t)b * p.T + tA) * Nw;
+      const float* nzB = p.noise + ((size_t)b * p.T + tB) * Nw;
+#pragma unroll
+      for (int n1 = 0; n1 < F::NROW; ++n1)
+        if (row_valid<NFFT, NW>(n1, n2, Nw)) {
+          const int j = G::R2 * n1 + n2;
+          x[n1] = c2_fma(c2_make(validA ? __ldg(nzA + j) : 0.f, validB ? __ldg(nzB + j) : 0.f), c2_splat(p.dither), x[n1]);
+        }
+    } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call)
+      const float d2 = p.dither * p.dither;
+      const float sgn = p.dither < 0.f ? -1.f : 1.f;
+#pragma unroll
+      for (int c5 = 0; c5 * 5 < F::NROW; ++c5) {
+        const uint4 rA = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)tA, (uint32_t)b, 0x5eedu),
+                                      p.seed_lo, p.seed_hi);
+        const uint4 rB = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)tB, (uint32_t)b, 0x5eedu),
+                                      p.seed_lo, p.seed_hi);
+        const uint32_t vA[5] = {rA.x >> 8, rA.y >> 8, rA.z >> 8, rA.w >> 8,
+                                ((rA.x & 0xffu) << 16) | ((rA.y & 0xffu) << 8) | (rA.z & 0xffu)};
+        const uint32_t vB[5] = {rB.x >> 8, rB.y >> 8, rB.z >> 8, rB.w >> 8,
+                                ((rB.x & 0xffu) << 16) | ((rB.y & 0xffu) << 8) | (rB.z & 0xffu)};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int n1 = 5 * c5 + i;
+          if (n1 < F::NROW) {
+            // dither * sqrt(-2 ln u) cos(2 pi u) for both frames; the MUFU ops are scalar, the rest packed
+            const float uA = (float)max(vA[i], 2u), uB = (float)max(vB[i], 2u);
+            const c2 a = c2_fma(c2_make(fast_log2(uA), fast_log2(uB)), c2_splat(-1.3862943611198906f * d2),
+                                c2_splat(33.27106466687737f * d2));
+            const c2 ang = c2_mul(c2_make(uA, uB), c2_splat(3.7450703370559213e-07f));  // 2 pi 2^-24
+            float csA, csB;
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csA) : "f"(c2_re(ang)));
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csB) : "f"(c2_im(ang)));
+            const c2 g = c2_mul(c2_make(fast_sqrt(c2_re(a)), fast_sqrt(c2_im(a))), c2_make(csA * sgn, csB * sgn));
+            if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = x[n1] + g;
+          }
+        }
+      }
+    }
+  }
+  c2 sum = x[0];
+#pragma unroll
+  for (int n1 = 1; n1 < F::NROW; ++n1) sum = sum + x[n1];
+  c2 mean = c2_splat(0.f);
+  if (p.remove_dc)
+    mean = c2_mul(c2_make(group_sum(c2_re(sum), G::R2), group_sum(c2_im(sum), G::R2)), c2_splat(1.0f / (float)Nw));
+  if (p.use_energy) {
+    c2 e = c2_splat(0.f);
+#pragma unroll
+    for (int n1 = 0; n1 < F::NROW; ++n1) {
+      const c2 d = row_valid<NFFT, NW>(n1, n2, Nw) ? x[n1] - mean : c2_splat(0.f);
+      e = c2_fma(d, d, e);
+    }
+    const float eA = group_sum(c2_re(e), G::R2), eB = group_sum(c2_im(e), G::R2);
+    if (n2 == 0) {
+      energy_slots[0] = fast_log(fmaxf(eA, kEps));
+      energy_slots[1] = fast_log(fmaxf(eB, kEps));
+    }
+  }
+  const float c = p.preemph;
+  const c2 mu = c2_mul(mean, c2_splat(1.0f - c));
+  const c2 mc = c2_splat(-c);
+  [[maybe_unused]] c2 rot_prev = c2_splat(0.f);
+#pragma unroll
+  for (int n1 = 0; n1 < F::NROW; ++n1) {
+    c2 prev;
+    if constexpr (NOISE) {
+      // previous sample of the noisy frame: the neighbouring lane's x[n1]; lane 0 takes the last lane's
+      // x[n1 - 1], i.e. what it received from the previous row's rotation (j == 0: replicate padding)
+      const int src = (n2 + G::R2 - 1) & (G::R2 - 1);
+      const c2 rot = c2_make(__shfl_sync(0xffffffffu, c2_re(x[n1]), src, G::R2),
+                             __shfl_sync(0xffffffffu, c2_im(x[n1]), src, G::R2));
+      const c2 wrap = n1 == 0 ? x[0] : rot_prev;
+      prev = (n2 == 0) ? wrap : rot;
+      rot_prev = rot;
+    } else {
+      const int j = G::R2 * n1 + n2;
+      const int jp = (row_valid<NFFT, NW>(n1, n2, Nw) ? j : 1) - 1;
+      prev = (n1 == 0 && n2 == 0) ? x[0] : c2_make(frA[jp], frB[jp]);
+    }
+    const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
+    const float wj = rv ? win[G::R2 * n1 + n2] : 0.f;
+    z[n1] = c2_mul(c2_fma(prev, mc, x[n1]) - mu, c2_splat(wj));
+  }
+  (void)validA;
+  (void)validB;
 }
 
 }  // namespace spl

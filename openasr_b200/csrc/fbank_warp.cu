@@ -98,7 +98,12 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   const int B = p.B, T = p.T, OP = L.op;
   TR(0);
 #ifdef SPL_TRACE
-  if (lane == 0) g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 1] = gtimer();
+  if (lane == 0) {
+    g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 1] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 26] = smid;
+  }
   int tr_it = 0;
 #endif
   float* wr = smem + L.off_warp + w * L.rw;  // this warp's region
@@ -160,7 +165,10 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   // floor(total * i / G) = q i + floor(r i / G) with total = q G + r: 32-bit divisions only (a 64-bit
   // division costs ~500 cycles of a single thread while the whole CTA waits).
   if (tid == 0 || tid == 32) {
-    const unsigned G = gridDim.x, bid = blockIdx.x;
+    // CTAs c and c + G/2 are co-resident on one SM (two CTAs per SM, breadth-first placement): give
+    // them consecutive shares so that every SM gets floor or ceil of the same 2/G of the work
+    const unsigned G = gridDim.x;
+    const unsigned bid = (G & 1u) ? blockIdx.x : 2u * (blockIdx.x % (G >> 1)) + blockIdx.x / (G >> 1);
     auto share = [&](long long total, unsigned i) -> int {
       if (total < 0x7fffffffLL && G < 0x10000u) {
         const unsigned t32 = (unsigned)total, q = t32 / G, r = t32 - q * G;
@@ -263,38 +271,6 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   if (g_cur < g1) stage_group(g_cur, cur);
   TR(25);
 
-  // ---- zero padding rows: an equal share of the padded rows per CTA (sp_layers.py:88), written while
-  // the first group's samples are in flight ----
-  {
-    int q = ctl[3];
-    const int q1 = ctl[4];
-    if (q < q1) {
-      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
-      }
-      int b = lo;
-      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
-      while (q < q1) {
-        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
-        const int m_b = fpre[b + 1] - fpre[b];
-        const int ofs = q - (b * T - fpre[b]);
-        int nrows = (T - m_b) - ofs;
-        nrows = nrows > q1 - q ? q1 - q : nrows;
-        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
-        if (vec) {
-          float4* d4 = reinterpret_cast<float4*>(dst);
-          const int n4 = nrows * (D_out >> 2);
-          for (int i = tid; i < n4; i += kWThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          for (int i = tid; i < nrows * D_out; i += kWThreads) dst[i] = 0.f;
-        }
-        q += nrows;
-      }
-    }
-  }
-
   TR(2);
   mbar_wait(bars, 0);  // tables have landed (the first group's samples are already in flight)
   TR(3);
@@ -324,7 +300,9 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       __syncwarp();
     }
 
-    // ---- stage 1: radix-16 over n1 (lane = n2), twiddle, transpose through the exchange planes ----
+    // ---- stage 1: radix-16 over n1 (lane = n2), twiddle, transpose through the exchange planes.
+    // Frames (t0, t0 + 1) and (t0 + 2, t0 + 3) are the (re, im) halves of two packed complex FFTs;
+    // all arithmetic runs on the fp32x2 pipe (fft_c2.cuh) ----
     if constexpr (NFFT == 512) {
       const int n2 = lane;
       float twr[16], twi[16];
@@ -333,51 +311,49 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         twr[k1] = tws[k1 * G::R2 + n2];
         twi[k1] = tws[NFFT + k1 * G::R2 + n2];
       }
-      float re[16], im[16], re1[16], im1[16];
-      load_frame_p<NFFT, NW, NOISE>(re, p, sbase, win, energy + 0, n2, cur.b, cur.t0, true);
-      load_frame_p<NFFT, NW, NOISE>(im, p, sbase + S, win, energy + 1, n2, cur.b, cur.t0 + 1, n > 1);
-      fft_dif<16, F::NROW>(re, im);
+      c2 z0[16], z1[16];
+      load_frame_pair<NFFT, NW, NOISE>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0, cur.t0 + 1, true,
+                                       n > 1);
+      fft_dif_c<16, F::NROW>(z0);
       {
         float* er = e0 + n2 * G::EP;
         float* ei = er + G::PL;
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
-          const float vr = re[bitrev<16>(k1)], vi = im[bitrev<16>(k1)];
-          er[k1] = vr * twr[k1] + vi * twi[k1];  // * (c - i s)
-          ei[k1] = vi * twr[k1] - vr * twi[k1];
+          const c2 o = c2_mulw(z0[bitrev<16>(k1)], twr[k1], twi[k1]);  // * (c - i s)
+          er[k1] = c2_re(o);
+          ei[k1] = c2_im(o);
         }
       }
-      load_frame_p<NFFT, NW, NOISE>(re1, p, sbase + 2 * S, win, energy + 2, n2, cur.b, cur.t0 + 2, n > 2);
-      load_frame_p<NFFT, NW, NOISE>(im1, p, sbase + 3 * S, win, energy + 3, n2, cur.b, cur.t0 + 3, n > 3);
+      load_frame_pair<NFFT, NW, NOISE>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b, cur.t0 + 2,
+                                       cur.t0 + 3, n > 2, n > 3);
       __syncwarp();  // every lane has its samples in registers: pair 1's planes may overwrite the buffer
-      fft_dif<16, F::NROW>(re1, im1);
+      fft_dif_c<16, F::NROW>(z1);
       {
         float* er = e1 + n2 * G::EP;
         float* ei = er + G::PL;
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
-          const float vr = re1[bitrev<16>(k1)], vi = im1[bitrev<16>(k1)];
-          er[k1] = vr * twr[k1] + vi * twi[k1];
-          ei[k1] = vi * twr[k1] - vr * twi[k1];
+          const c2 o = c2_mulw(z1[bitrev<16>(k1)], twr[k1], twi[k1]);
+          er[k1] = c2_re(o);
+          ei[k1] = c2_im(o);
         }
       }
     } else {
       const int pr = lane >> 4, n2 = lane & 15;
       const int fa = 2 * pr;
-      float re[16], im[16];
-      load_frame_p<NFFT, NW, NOISE>(re, p, sbase + fa * S, win, energy + fa, n2, cur.b, cur.t0 + fa, fa < n);
-      load_frame_p<NFFT, NW, NOISE>(im, p, sbase + (fa + 1) * S, win, energy + fa + 1, n2, cur.b, cur.t0 + fa + 1,
-                                    fa + 1 < n);
+      c2 z[16];
+      load_frame_pair<NFFT, NW, NOISE>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
+                                       cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n);
       __syncwarp();  // samples are in registers; pair 1's planes alias the buffer
-      fft_dif<16, F::NROW>(re, im);
+      fft_dif_c<16, F::NROW>(z);
       float* er = (pr ? e1 : e0) + n2 * G::EP;
       float* ei = er + G::PL;
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
-        const float cs = tws[k1 * G::R2 + n2], sn = tws[NFFT + k1 * G::R2 + n2];
-        const float vr = re[bitrev<16>(k1)], vi = im[bitrev<16>(k1)];
-        er[k1] = vr * cs + vi * sn;
-        ei[k1] = vi * cs - vr * sn;
+        const c2 o = c2_mulw(z[bitrev<16>(k1)], tws[k1 * G::R2 + n2], tws[NFFT + k1 * G::R2 + n2]);
+        er[k1] = c2_re(o);
+        ei[k1] = c2_im(o);
       }
     }
     __syncwarp();
@@ -385,38 +361,34 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
 
     // ---- stage 2: lane = (pair, k1), registers = n2 ----
     const int pr = lane >> 4, k1 = lane & 15;
-    float xr[G::R2], xi[G::R2];
+    c2 x[G::R2];
     {
       const float* er = (pr ? e1 : e0) + k1;
       const float* ei = er + G::PL;
 #pragma unroll
-      for (int n2 = 0; n2 < G::R2; ++n2) {
-        xr[n2] = er[n2 * G::EP];
-        xi[n2] = ei[n2 * G::EP];
-      }
+      for (int n2 = 0; n2 < G::R2; ++n2) x[n2] = c2_make(er[n2 * G::EP], ei[n2 * G::EP]);
     }
     __syncwarp();  // exchange planes dead: pair 0's area becomes the power rows, pair 1's the next samples
     if (g_nxt < g1) stage_group(g_nxt, nxt);
-    fft_dif<G::R2>(xr, xi);
+    fft_dif_c<G::R2>(x);
 
-    // Hermitian partner + power: Z[k1 + 16 k2] sits at register bitrev(k2)
+    // Hermitian partner + power: Z[k1 + 16 k2] sits at register bitrev(k2).  With q = Z[N - k]:
+    //   2 X_a = (zr + qr, zi - qi),  2 X_b = (zi + qi, qr - zr)   (frames a / b of the pair)
+    //   S = Z + q = (ar, br),  D = Z - q = (-bi, ai)  ->  (4|X_a|^2, 4|X_b|^2) = S*S + swap(D)*swap(D)
     {
       const int partner = (lane & 16) | ((16 - k1) & 15);
       float* pa = e0 + (2 * pr) * G::PP + k1;
       float* pb = pa + G::PP;
 #pragma unroll
       for (int k2 = 0; k2 < G::H; ++k2) {
-        const float zr = xr[bitrev<G::R2>(k2)], zi = xi[bitrev<G::R2>(k2)];
-        float qr = __shfl_sync(0xffffffffu, xr[bitrev<G::R2>(G::R2 - 1 - k2)], partner);
-        float qi = __shfl_sync(0xffffffffu, xi[bitrev<G::R2>(G::R2 - 1 - k2)], partner);
-        if (k1 == 0) {
-          qr = xr[bitrev<G::R2>((G::R2 - k2) & (G::R2 - 1))];
-          qi = xi[bitrev<G::R2>((G::R2 - k2) & (G::R2 - 1))];
-        }
-        const float ar = zr + qr, ai = zi - qi;
-        const float br = zi + qi, bi = qr - zr;
-        pa[16 * k2] = ar * ar + ai * ai;  // 4 |X_A|^2 (the 1/4 is folded into the mel weights)
-        pb[16 * k2] = br * br + bi * bi;
+        const c2 zv = x[bitrev<G::R2>(k2)];
+        const c2 qs = x[bitrev<G::R2>(G::R2 - 1 - k2)];
+        c2 q = c2_make(__shfl_sync(0xffffffffu, c2_re(qs), partner), __shfl_sync(0xffffffffu, c2_im(qs), partner));
+        if (k1 == 0) q = x[bitrev<G::R2>((G::R2 - k2) & (G::R2 - 1))];
+        const c2 sv = zv + q, dv = c2_swap(zv - q);
+        const c2 pw = c2_fma(dv, dv, c2_mul(sv, sv));  // the 1/4 is folded into the mel weights
+        pa[16 * k2] = c2_re(pw);
+        pb[16 * k2] = c2_im(pw);
       }
     }
     __syncwarp();
@@ -434,18 +406,15 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         const uint32_t dsc = pdesc[8 * j + sl];
         const float4* pa4 = prow4 + (dsc & 63u);
         const float4* pb4 = prow4 + ((dsc >> 6) & 63u);
-        float accA = 0.f, accB = 0.f;
+        c2 accA = c2_splat(0.f), accB = c2_splat(0.f);  // (x + z, y + w) partial sums of the 4-bin groups
         auto mac = [&](int g) {
-          const float4 pa = pa4[g], pb = pb4[g];
-          const float4 wa = wv[16 * g], wb = wv[16 * g + 8];
-          accA = fmaf(pa.x, wa.x, accA);
-          accB = fmaf(pb.x, wb.x, accB);
-          accA = fmaf(pa.y, wa.y, accA);
-          accB = fmaf(pb.y, wb.y, accB);
-          accA = fmaf(pa.z, wa.z, accA);
-          accB = fmaf(pb.z, wb.z, accB);
-          accA = fmaf(pa.w, wa.w, accA);
-          accB = fmaf(pb.w, wb.w, accB);
+          const ulonglong2 pa = reinterpret_cast<const ulonglong2*>(pa4)[g], pb = reinterpret_cast<const ulonglong2*>(pb4)[g];
+          const ulonglong2 wa = reinterpret_cast<const ulonglong2*>(wv)[16 * g],
+                           wb = reinterpret_cast<const ulonglong2*>(wv)[16 * g + 8];
+          accA = c2_fma(c2{pa.x}, c2{wa.x}, accA);
+          accB = c2_fma(c2{pb.x}, c2{wb.x}, accB);
+          accA = c2_fma(c2{pa.y}, c2{wa.y}, accA);
+          accB = c2_fma(c2{pb.y}, c2{wb.y}, accB);
         };
         int g = 0;
 #pragma unroll 1
@@ -455,8 +424,8 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         }
         if (g < n4) mac(g);
         const int m0 = 2 * (8 * j + sl);
-        if (dsc & 0x40000000u) orow[m0] = fast_log(fmaxf(accA, kEps));  // kaldi_signal.py:540
-        if (dsc & 0x80000000u) orow[m0 + 1] = fast_log(fmaxf(accB, kEps));
+        if (dsc & 0x40000000u) orow[m0] = fast_log(fmaxf(c2_re(accA) + c2_im(accA), kEps));  // kaldi_signal.py:540
+        if (dsc & 0x80000000u) orow[m0 + 1] = fast_log(fmaxf(c2_re(accB) + c2_im(accB), kEps));
       }
       if (p.use_energy && lane < 4) orows[lane * OP] = energy[lane];
     }
@@ -470,7 +439,16 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         const int q = D_out >> 2;  // OP == D_out here: the rows are contiguous in shared memory too
         const float4* src = reinterpret_cast<const float4*>(orows);
         float4* dst = reinterpret_cast<float4*>(out_g);
-        for (int i = lane; i < n * q; i += 32) dst[i] = src[i];
+        const int tot = n * q;
+        for (int i0 = lane; i0 < tot; i0 += 128) {  // four independent 16-byte copies in flight per lane
+          float4 tmp[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < tot) tmp[u] = src[i0 + 32 * u];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < tot) dst[i0 + 32 * u] = tmp[u];
+        }
       } else {
         for (int r = 0; r < n; ++r)
           for (int c = lane; c < D_out; c += 32) out_g[(size_t)r * D_out + c] = orows[r * OP + c];
@@ -481,15 +459,34 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
           stat_b = cur.b;
         }
         stat_rows += n;
-        for (int c = lane; c < D_out; c += 32) {
-          double a1 = wstat[c], a2 = wstat[OP + c];
-          for (int r = 0; r < n; ++r) {
-            const double v = (double)orows[r * OP + c];
-            a1 += v;
-            a2 = fma(v, v, a2);
+        for (int c0 = lane; c0 < D_out; c0 += 96) {  // three columns per lane: independent fp64 chains
+          double a1[3], a2[3];
+          float v[3][4];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int c = c0 + 32 * k;
+            const bool cv = c < D_out;
+            a1[k] = cv ? wstat[c] : 0.0;
+            a2[k] = cv ? wstat[OP + c] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[k][r] = (cv && r < n) ? orows[r * OP + c] : 0.f;
           }
-          wstat[c] = a1;
-          wstat[OP + c] = a2;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const double d = (double)v[k][r];
+              a1[k] += d;
+              a2[k] = fma(d, d, a2[k]);
+            }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int c = c0 + 32 * k;
+            if (c < D_out) {
+              wstat[c] = a1[k];
+              wstat[OP + c] = a2[k];
+            }
+          }
         }
       }
     }
@@ -503,6 +500,39 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   }
 
   TR(30);
+  // ---- zero padding rows (sp_layers.py:88): the CTA's equal share of the batch's padded rows, one
+  // eighth per warp, written after the warp's last group -- off the critical path, since the warps
+  // that ran out of groups early would otherwise idle at the final barrier ----
+  {
+    const int q0 = ctl[3], qn = ctl[4] - q0;
+    int q = q0 + (int)((long long)qn * w / kWWarps);
+    const int q1 = q0 + (int)((long long)qn * (w + 1) / kWWarps);
+    if (q < q1) {
+      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+      }
+      int b = lo;
+      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
+      while (q < q1) {
+        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
+        const int m_b = fpre[b + 1] - fpre[b];
+        const int ofs = q - (b * T - fpre[b]);
+        int nrows = (T - m_b) - ofs;
+        nrows = nrows > q1 - q ? q1 - q : nrows;
+        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
+        if (vec) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const int n4 = nrows * (D_out >> 2);
+          for (int i = lane; i < n4; i += 32) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int i = lane; i < nrows * D_out; i += 32) dst[i] = 0.f;
+        }
+        q += nrows;
+      }
+    }
+  }
   // ---- epilogue: the warps' running sums (one utterance each) are merged by column, without
   // shared-memory atomics: thread i owns entry i of the [2][OP] rows and walks the 8 warps ----
   if (want_stats) {

@@ -16,8 +16,9 @@ namespace spl {
 constexpr int kPostRows = 64;  // rows of one utterance per CTA
 constexpr int kPostThreads = 256;
 
-template <bool VEC4>
-__global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) {
+// VEC4: rows are float4-addressable; NG: float4 groups per lane (1: Dm <= 128, 2: Dm <= 256)
+template <bool VEC4, int NG>
+__global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams p) {
   __shared__ __align__(16) float s_mean[kMaxDm];
   __shared__ __align__(16) float s_istd[kMaxDm];
   __shared__ __align__(16) float s_tm[kMaxDm];
@@ -25,24 +26,31 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
   const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Dm = p.Dm;
-  const int len = (int)p.feat_len[b];
   const int nmask = p.mask_params ? (p.n_freq + p.n_time) : 0;
+  // every global load of the prologue is issued before the first use (one L2 round trip, not three)
+  const long long len64 = p.feat_len[b];
+  double s1 = 0.0, s2 = 0.0;
+  if (p.utt_stats && tid < Dm) {
+    s1 = p.utt_stats[((size_t)b * 2 + 0) * Dm + tid];
+    s2 = p.utt_stats[((size_t)b * 2 + 1) * Dm + tid];
+  }
+  int my_mask = 0;
+  if (tid < 2 * nmask) my_mask = p.mask_params[(size_t)b * 2 * nmask + tid];
+  const int len = (int)len64;
 
   // rows this CTA has to touch: valid rows, plus padding rows hit by a (spilled) time mask
+  if (tid < 2 * nmask) s_mask[tid] = my_mask;
+  __syncthreads();
   int t_hi = len;
   for (int j = p.n_freq; j < nmask; ++j) {
-    const int e = p.mask_params[((size_t)b * nmask + j) * 2 + 1];
+    const int e = s_mask[2 * j + 1];
     t_hi = e > t_hi ? e : t_hi;
   }
   if (t0 >= t_hi) return;
 
-  for (int d = tid; d < Dm; d += kPostThreads) {
+  if (tid < Dm) {
+    const int d = tid;
     float mean = 0.f, istd = 1.f;
-    double s1 = 0.0, s2 = 0.0;
-    if (p.utt_stats) {
-      s1 = p.utt_stats[((size_t)b * 2 + 0) * Dm + d];
-      s2 = p.utt_stats[((size_t)b * 2 + 1) * Dm + d];
-    }
     const double inv_len = len > 0 ? 1.0 / (double)len : 0.0;
     const double umean = s1 * inv_len;
     if (p.cmvn_mode == SPL_CMVN_UTTERANCE) {
@@ -58,88 +66,118 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     s_istd[d] = istd;
     s_tm[d] = (float)((umean - (double)mean) * (double)istd);  // time mean of the normalised features
   }
-  for (int i = tid; i < 2 * nmask; i += kPostThreads) s_mask[i] = p.mask_params[(size_t)b * 2 * nmask + i];
   __syncthreads();
 
   const int tend = min(min(t0 + kPostRows, p.T), t_hi);
   const float inv_d = 1.0f / (float)Dm;
-  for (int t = t0 + w; t < tend; t += kPostThreads / 32) {
-    float* row = p.feats + ((size_t)b * p.T + t) * Dm;
-    bool tmask = false;
-    for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
+  const bool need_fm = p.n_freq > 0 && nmask > 0;
+  constexpr int kWarpsB = kPostThreads / 32;
+  constexpr int RB = 4;  // rows in flight per warp: their loads are issued together (one L2 round trip, not four)
+  for (int tb = t0 + w; tb < tend; tb += RB * kWarpsB) {
     if (VEC4) {
-      // Dm % 4 == 0, rows 16-byte aligned: lane handles float4 groups lane, lane + 32 (Dm <= 256)
-      float4* row4 = reinterpret_cast<float4*>(row);
+      // Dm % 4 == 0, rows 16-byte aligned: lane handles float4 groups lane (+ 32 when NG == 2)
       const int q = Dm >> 2;
-      if (tmask) {  // may legitimately touch padding rows (reference quirk for len < width)
-        for (int g = lane; g < q; g += 32) row4[g] = reinterpret_cast<const float4*>(s_tm)[g];
-        continue;
-      }
-      if (t >= len) continue;  // padding: stays exactly 0 (freq means of a zero row are 0)
-      float4 y[2];
-      float sum = 0.f;
+      float4 x[RB][NG];
+      bool tm[RB], live[RB];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int g = lane + 32 * i;
-        y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < q) {
-          const float4 x = row4[g], m = reinterpret_cast<const float4*>(s_mean)[g],
-                       s = reinterpret_cast<const float4*>(s_istd)[g];
-          y[i] = make_float4((x.x - m.x) * s.x, (x.y - m.y) * s.y, (x.z - m.z) * s.z, (x.w - m.w) * s.w);
-          sum += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+      for (int r = 0; r < RB; ++r) {
+        const int t = tb + r * kWarpsB;
+        bool tmask = false;
+        for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
+        tm[r] = tmask && t < tend;
+        live[r] = t < tend && !tmask && t < len;  // padding stays exactly 0 (freq means of a zero row are 0)
+        const float4* row4 = reinterpret_cast<const float4*>(p.feats + ((size_t)b * p.T + t) * Dm);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          const int g = lane + 32 * i;
+          x[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live[r] && g < q) x[r][i] = row4[g];
         }
       }
-      float fm = 0.f;
-      if (p.n_freq > 0 && nmask > 0) {
+      float sum[RB];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        fm = sum * inv_d;
+      for (int r = 0; r < RB; ++r) {
+        sum[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          const int g = lane + 32 * i;
+          if (g < q) {
+            const float4 m = reinterpret_cast<const float4*>(s_mean)[g], sd = reinterpret_cast<const float4*>(s_istd)[g];
+            float4& v = x[r][i];
+            v = make_float4((v.x - m.x) * sd.x, (v.y - m.y) * sd.y, (v.z - m.z) * sd.z, (v.w - m.w) * sd.w);
+            sum[r] += (v.x + v.y) + (v.z + v.w);
+          }
+        }
+      }
+      if (need_fm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int r = 0; r < RB; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int g = lane + 32 * i;
-        if (g < q) {
-          float v[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
-          for (int j = 0; j < p.n_freq && j < nmask; ++j) {
-            const int f0 = s_mask[2 * j], f1 = s_mask[2 * j + 1];
+      for (int r = 0; r < RB; ++r) {
+        const int t = tb + r * kWarpsB;
+        float4* row4 = reinterpret_cast<float4*>(p.feats + ((size_t)b * p.T + t) * Dm);
+        if (tm[r]) {  // may legitimately touch padding rows (reference quirk for len < width)
+          for (int g = lane; g < q; g += 32) row4[g] = reinterpret_cast<const float4*>(s_tm)[g];
+          continue;
+        }
+        if (!live[r]) continue;
+        const float fm = need_fm ? sum[r] * inv_d : 0.f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (4 * g + e >= f0 && 4 * g + e < f1) v[e] = fm;
+        for (int i = 0; i < NG; ++i) {
+          const int g = lane + 32 * i;
+          if (g < q) {
+            float v[4] = {x[r][i].x, x[r][i].y, x[r][i].z, x[r][i].w};
+            for (int j = 0; j < p.n_freq && j < nmask; ++j) {
+              const int f0 = s_mask[2 * j], f1 = s_mask[2 * j + 1];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (4 * g + e >= f0 && 4 * g + e < f1) v[e] = fm;
+            }
+            row4[g] = make_float4(v[0], v[1], v[2], v[3]);
           }
-          row4[g] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     } else {
-      if (tmask) {
-        for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
-        continue;
-      }
-      if (t >= len) continue;
-      float y[kMaxDm / 32];
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < kMaxDm / 32; ++i) {
-        const int d = lane + 32 * i;
-        y[i] = 0.f;
-        if (d < Dm) {
-          y[i] = (row[d] - s_mean[d]) * s_istd[d];
-          sum += y[i];
+      for (int r = 0; r < RB; ++r) {
+        const int t = tb + r * kWarpsB;
+        if (t >= tend) break;
+        float* row = p.feats + ((size_t)b * p.T + t) * Dm;
+        bool tmask = false;
+        for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
+        if (tmask) {
+          for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
+          continue;
         }
-      }
-      float fm = 0.f;
-      if (p.n_freq > 0 && nmask > 0) {
+        if (t >= len) continue;
+        float y[kMaxDm / 32];
+        float sum = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        fm = sum * inv_d;
-      }
+        for (int i = 0; i < kMaxDm / 32; ++i) {
+          const int d = lane + 32 * i;
+          y[i] = 0.f;
+          if (d < Dm) {
+            y[i] = (row[d] - s_mean[d]) * s_istd[d];
+            sum += y[i];
+          }
+        }
+        float fm = 0.f;
+        if (need_fm) {
 #pragma unroll
-      for (int i = 0; i < kMaxDm / 32; ++i) {
-        const int d = lane + 32 * i;
-        if (d < Dm) {
-          float v = y[i];
-          for (int j = 0; j < p.n_freq && j < nmask; ++j)
-            if (d >= s_mask[2 * j] && d < s_mask[2 * j + 1]) v = fm;
-          row[d] = v;
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          fm = sum * inv_d;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxDm / 32; ++i) {
+          const int d = lane + 32 * i;
+          if (d < Dm) {
+            float v = y[i];
+            for (int j = 0; j < p.n_freq && j < nmask; ++j)
+              if (d >= s_mask[2 * j] && d < s_mask[2 * j + 1]) v = fm;
+            row[d] = v;
+          }
         }
       }
     }
@@ -149,10 +187,12 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
 cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
   dim3 grid((p.T + kPostRows - 1) / kPostRows, p.B);
   const bool vec = (p.Dm & 3) == 0 && p.Dm <= 256 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
-  if (vec)
-    post_kernel<true><<<grid, kPostThreads, 0, st>>>(p);
+  if (vec && p.Dm <= 128)
+    post_kernel<true, 1><<<grid, kPostThreads, 0, st>>>(p);
+  else if (vec)
+    post_kernel<true, 2><<<grid, kPostThreads, 0, st>>>(p);
   else
-    post_kernel<false><<<grid, kPostThreads, 0, st>>>(p);
+    post_kernel<false, 1><<<grid, kPostThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 

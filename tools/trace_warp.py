@@ -63,3 +63,20 @@ for it in range(4):
     base = 4 + 6 * it
     its += ((t[:, :, base] > t[:, :, 0]) & (rel[:, :, base] < rel[:, :, 30])).astype(int)
 print("groups per warp histogram:", np.bincount(its.ravel()))
+
+# per-SM view: which CTAs share an SM, when each SM finishes, and how many groups it ran
+smid = t[:, 0, 26]
+gt0 = t[:, :, 1].min()
+cta_start_ns = t[:, :, 1].min(axis=1) - gt0
+cta_groups = its.sum(axis=1)
+sm_end = {}
+for c in range(296):
+    sm_end.setdefault(int(smid[c]), []).append((int(cta_end[c]), int(cta_groups[c]), int(cta_start_ns[c]), c))
+ends = sorted(((max(e for e, _, _, _ in v), sum(g for _, g, _, _ in v), len(v), [x[3] for x in v]) for v in sm_end.values()))
+print("SMs used: %d; CTAs per SM histogram: %s" % (len(sm_end), np.bincount([len(v) for v in sm_end.values()])))
+print("fastest SMs (end cycles, groups, ctas):", ends[:4])
+print("slowest SMs (end cycles, groups, ctas):", ends[-6:])
+print("late-starting CTAs (start ns > 1000):", [(c, int(cta_start_ns[c]), int(smid[c])) for c in range(296) if cta_start_ns[c] > 1000][:20])
+g_by_sm = np.array([e[1] for e in ends]); e_by_sm = np.array([e[0] for e in ends])
+for g in sorted(set(g_by_sm)):
+    print("  SMs with %d groups: %d, median end %.0f" % (g, (g_by_sm == g).sum(), np.median(e_by_sm[g_by_sm == g])))
