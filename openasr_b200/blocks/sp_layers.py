@@ -205,17 +205,20 @@ class SPLayer(nn.Module):
             nf, nt = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
             u = frontend.specaug_uniforms(B, nf, nt, None).numpy()
             arrays.append(frontend.specaug_rectangles_c(u, frames_np, T, h.d_out, conf))
-        keep, ptrs = self._stager.upload(arrays, dev)
+        stream = torch.cuda.current_stream(dev)  # looked up once: every launch of this call goes there
+        sptr = frontend.C.c_void_p(stream.cuda_stream)
+        keep, ptrs = self._stager.upload(arrays, dev, stream)
         utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
         feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
-        h.fbank(wav_batch, ptrs[0], T, dither_seed=seed, utt_stats=utt_stats, out=feats, feat_len=feat_len)
+        h.fbank(wav_batch, ptrs[0], T, dither_seed=seed, utt_stats=utt_stats, out=feats, feat_len=feat_len,
+                stream_ptr=sptr)
         if self._cmvn != "none" or aug:
             if self._cmvn == "global" and self._gmean is None:
                 raise RuntimeError("cmvn='global' needs set_global_cmvn() (see openasr_b200.cmvn)")
             frontend.post_inplace(feats, feat_len, cmvn_mode=self._cmvn, norm_vars=self._cmvn_norm_vars,
                                   utt_stats=utt_stats, global_mean=self._gmean, global_istd=self._gistd,
-                                  mask_params=ptrs[1] if aug else None, n_freq=nf, n_time=nt)
+                                  mask_params=ptrs[1] if aug else None, n_freq=nf, n_time=nt, handle=h, stream_ptr=sptr)
         del keep  # stream-ordered allocator: the block is only reused behind the launches above
         return feats, feat_len
 

@@ -66,8 +66,8 @@ class FbankHandle:
     def fbank(self, wav: torch.Tensor, wav_len_dev: torch.Tensor, T: int, *,
               noise: Optional[torch.Tensor] = None, dither_seed: int = 0,
               utt_stats: Optional[torch.Tensor] = None, global_stats: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None, feat_len: Optional[torch.Tensor] = None
-              ) -> Tuple[torch.Tensor, torch.Tensor]:
+              out: Optional[torch.Tensor] = None, feat_len: Optional[torch.Tensor] = None,
+              stream_ptr: Optional[C.c_void_p] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """wav [B, L] (fp32 or int16, int16-scaled) + device int64 lengths -> feats [B, T, D_out], feat_len [B]."""
         _require_cuda(wav, "wav_batch")
         if wav.dim() != 2:
@@ -100,7 +100,8 @@ class FbankHandle:
         a.dither_seed = dither_seed & 0xFFFFFFFFFFFFFFFF
         a.utt_stats = utt_stats.data_ptr() if utt_stats is not None else None
         a.global_stats = global_stats.data_ptr() if global_stats is not None else None
-        _capi.check(self._lib.spl_fbank_forward(self._h, C.byref(a), _stream_ptr(dev)), "spl_fbank_forward")
+        _capi.check(self._lib.spl_fbank_forward(self._h, C.byref(a), stream_ptr or _stream_ptr(dev)),
+                    "spl_fbank_forward")
         return out, feat_len
 
 
@@ -122,8 +123,10 @@ def get_handle(device: torch.device, sample_rate: float, num_mel_bins: int, use_
 def post_inplace(feats: torch.Tensor, feat_len: torch.Tensor, *, cmvn_mode: str = "none",
                  norm_vars: bool = True, utt_stats: Optional[torch.Tensor] = None,
                  global_mean: Optional[torch.Tensor] = None, global_istd: Optional[torch.Tensor] = None,
-                 mask_params: Optional[torch.Tensor] = None, n_freq: int = 0, n_time: int = 0) -> None:
-    """CMVN + SpecAug in place on a contiguous CUDA [B, T, D] fp32 tensor."""
+                 mask_params: Optional[torch.Tensor] = None, n_freq: int = 0, n_time: int = 0,
+                 handle: Optional["FbankHandle"] = None, stream_ptr: Optional[C.c_void_p] = None) -> None:
+    """CMVN + SpecAug in place on a contiguous CUDA [B, T, D] fp32 tensor.  With ``handle`` the library
+    selects the handle's device itself (no Python device context needed)."""
     _require_cuda(feats, "features")
     if feats.dtype != torch.float32 or not feats.is_contiguous():
         raise ValueError("features must be contiguous float32")
@@ -141,8 +144,13 @@ def post_inplace(feats: torch.Tensor, feat_len: torch.Tensor, *, cmvn_mode: str 
     a.n_freq_masks, a.n_time_masks = int(n_freq), int(n_time)
     a.mask_params = (mask_params if isinstance(mask_params, int) else mask_params.data_ptr()) \
         if mask_params is not None else None
+    if handle is not None:
+        _capi.check(lib.spl_post_inplace(handle._h, C.byref(a), stream_ptr or _stream_ptr(feats.device)),
+                    "spl_post_inplace")
+        return
     with torch.cuda.device(feats.device):
-        _capi.check(lib.spl_post_inplace(None, C.byref(a), _stream_ptr(feats.device)), "spl_post_inplace")
+        _capi.check(lib.spl_post_inplace(None, C.byref(a), stream_ptr or _stream_ptr(feats.device)),
+                    "spl_post_inplace")
 
 
 def column_stats(feats: torch.Tensor, feat_len: torch.Tensor) -> torch.Tensor:
@@ -256,11 +264,12 @@ class HostStager:
     def __init__(self, slots: int = 16, nbytes: int = 1 << 14):
         self._nslots, self._nbytes = slots, nbytes
         self._slots = None  # pinned memory needs a driver: allocate on first use
+        self._np = None     # numpy views of the slots
         self._events = [None] * slots
         self._next = 0
         self._lock = threading.Lock()
 
-    def upload(self, arrays, device: torch.device) -> Tuple[torch.Tensor, list]:
+    def upload(self, arrays, device: torch.device, stream=None) -> Tuple[torch.Tensor, list]:
         """arrays: list of contiguous numpy arrays (8-byte aligned sizes handled here).
         Returns (device uint8 tensor keeping the memory alive, list of device pointers)."""
         sizes = [(a.nbytes + 7) & ~7 for a in arrays]
@@ -268,13 +277,15 @@ class HostStager:
         with self._lock:
             if self._slots is None:
                 self._slots = [torch.empty(self._nbytes, dtype=torch.uint8).pin_memory() for _ in range(self._nslots)]
+                self._np = [t.numpy() for t in self._slots]
             i = self._next
             self._next = (i + 1) % len(self._slots)
         if total > self._slots[i].numel():
             self._slots[i] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
+            self._np[i] = self._slots[i].numpy()
         if self._events[i] is not None:
             self._events[i].synchronize()
-        host = self._slots[i].numpy()
+        host = self._np[i]
         offs, o = [], 0
         for a, sz in zip(arrays, sizes):
             host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
@@ -284,6 +295,6 @@ class HostStager:
         dev.copy_(self._slots[i][:total], non_blocking=True)
         if self._events[i] is None:
             self._events[i] = torch.cuda.Event()
-        self._events[i].record(torch.cuda.current_stream(device))
+        self._events[i].record(stream if stream is not None else torch.cuda.current_stream(device))
         base = dev.data_ptr()
         return dev, [base + x for x in offs]
