@@ -123,6 +123,17 @@ SPL_API int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream
 SPL_API int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len, int32_t B, int32_t T,
                      int32_t Dm, double* utt_stats, void* stream);
 
+/* Row f2: first layer of the conv-subsampling block on the [B, T, D] features, replacing
+ * Conv2d(1, C, 3, (2, 1)) + ReLU of src/blocks/conv_layers.py:125-126 ("subsample/conv0",
+ * "subsample/relu0") together with the unsqueeze(1) of :139:
+ *   out[b, c, t1, d1] = max(0, bias[c] + sum_{i,j<3} weight[c, 0, i, j] * feats[b, 2 t1 + i, d1 + j])
+ * feats [B, T, D] fp32 contiguous; weight [C, 1, 3, 3] and bias [C] (NULL = no bias) in torch's
+ * parameter layout; out [B, C, (T-3)/2+1, D-2] fp32 contiguous.  T >= 3, D >= 3, 1 <= C <= 64.
+ * `h` may be NULL (current device).  Rows t >= feat_len are convolved like any other row, exactly
+ * as the reference does on its zero-padded batch. */
+SPL_API int spl_conv0_relu(spl_handle* h, const float* feats, int32_t B, int32_t T, int32_t D, const float* weight,
+                           const float* bias, int32_t C, float* out, void* stream);
+
 /* Host-side helper (no device work): turn the 2*(F+T) x B uniforms drawn in the reference's order
  * (sp_layers.py:58-71) into [B, F+T, 2] half-open mask rectangles with the reference's float32
  * arithmetic and Python slice semantics.  `frames` = valid frames per utterance (host). */

@@ -69,7 +69,8 @@ class SplPostArgs(C.Structure):
 
 
 EXPORTS = ("spl_create", "spl_destroy", "spl_fbank_forward", "spl_post_inplace", "spl_column_stats",
-           "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest", "spl_specaug_rects")
+           "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest", "spl_specaug_rects",
+           "spl_conv0_relu")
 
 _lib = None
 
@@ -101,6 +102,9 @@ def load() -> C.CDLL:
     lib.spl_specaug_rects.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                       C.c_int32, C.c_float, C.c_void_p]
     lib.spl_specaug_rects.restype = C.c_int
+    lib.spl_conv0_relu.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_void_p, C.c_void_p]
+    lib.spl_conv0_relu.restype = C.c_int
     lib.spl_feature_dim.argtypes = [C.c_void_p]
     lib.spl_feature_dim.restype = C.c_int
     lib.spl_abi_version.argtypes = []

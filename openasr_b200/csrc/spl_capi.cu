@@ -600,6 +600,23 @@ int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len,
   return SPL_OK;
 }
 
+int spl_conv0_relu(spl_handle* h, const float* feats, int32_t B, int32_t T, int32_t D, const float* weight,
+                   const float* bias, int32_t C, float* out, void* stream) {
+  if (!feats || !weight || !out) return fail(SPL_ERR_INVALID_ARG, "spl_conv0_relu: null argument");
+  if (B < 1 || B > 65535 || T < 3 || D < 3 || C < 1 || C > 64)
+    return fail(SPL_ERR_INVALID_ARG, "spl_conv0_relu: need 1 <= B <= 65535, T >= 3, D >= 3, 1 <= C <= 64");
+  if ((long long)((T - 3) / 2 + 1) * (D - 2) > 0x7fffffffLL - 4096)
+    return fail(SPL_ERR_INVALID_ARG, "spl_conv0_relu: output plane too large");
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  DeviceGuard guard(h ? h->device : cur_dev);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_conv0_relu: cudaSetDevice failed");
+  cudaError_t e = spl::launch_conv0_relu(feats, weight, bias, out, B, T, D, C, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "spl_conv0_relu: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
+}
+
 // Host helper: SpecAug rectangles from the uniforms, same float32 arithmetic and truncation as
 // sp_layers.py:59-62 / :68-71 and Python slice semantics of x[b, s:s+w] (:64, :73).
 int spl_specaug_rects(const float* uniforms, const int64_t* frames, int32_t B, int32_t T, int32_t V, int32_t n_freq,

@@ -113,6 +113,10 @@ cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);
 
+// Conv2d(1 -> C, 3x3, stride (2, 1)) + ReLU on the [B, T, D] features (conv0_kernel.cu); C <= 64
+cudaError_t launch_conv0_relu(const float* x, const float* w, const float* bias, float* out, int B, int T, int D, int C,
+                              cudaStream_t st);
+
 // tcgen05 DFT-as-GEMM fbank kernel (fp32 samples, B <= kMaxPersistentB); one CTA per SM
 cudaError_t launch_fbank_tc(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
 size_t fbank_tc_smem_bytes(int nfft, int D_out, int tc_tab_words);

@@ -392,3 +392,72 @@ def test_concurrent_host_threads_same_device(wavs):
         t.join()
     for a, b in zip(serial, out):
         assert torch.equal(a, b)
+
+
+# --------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("sr,D,B,lo,hi", [(16000, 80, 32, 56000, 104000), (8000, 40, 64, 16000, 48000)])
+def test_full_size_invariances(sr, D, B, lo, hi):
+    """Size-independent properties at the BASELINE shapes (no oracle needed):
+    * a frame's features do not depend on where the utterance sits in the batch (bit-exact under a
+      batch permutation and against the utterance processed alone);
+    * time-shift equivariance: dropping the first 4 hops of samples drops the first 4 frames, every
+      other frame keeps its slot in its 4-frame group, so the values are bit-identical;
+    * dropping 1 hop moves frames to the other half of their packed FFT: equal to rounding error;
+    * padding rows are exact zeros and lengths exact at full size."""
+    x, lens = fo.synth_batch(B, lo, hi, sr, seed=11)
+    layer, conf = make_layer(sample_rate=sr, num_mel_bins=D)
+    layer.eval()
+    xc = x.cuda()
+    feats, flen = layer(xc, lens)
+    shift, win = layer._handle(xc.device).shift, layer._handle(xc.device).win
+    frames = 1 + (lens - win) // shift
+    assert torch.equal(flen.cpu(), frames)
+    for i in range(B):
+        assert (feats[i, frames[i]:] == 0).all()
+    # batch permutation
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+    fp, lp = layer(xc[perm.cuda()], lens[perm])
+    assert torch.equal(lp.cpu(), frames[perm])
+    assert torch.equal(fp, feats[perm.cuda()])
+    # one utterance alone
+    for i in (0, B // 2, B - 1):
+        n = int(lens[i])
+        fa, la = layer(xc[i:i + 1, :n].contiguous(), [n])
+        assert int(la[0]) == int(frames[i])
+        assert torch.equal(fa[0], feats[i, :int(frames[i])])
+    # shift by one group of 4 frames: bit-exact
+    f4, l4 = layer(xc[:, 4 * shift:].contiguous(), lens - 4 * shift)
+    assert torch.equal(l4.cpu(), frames - 4)
+    for i in range(B):
+        m = int(frames[i]) - 4
+        assert torch.equal(f4[i, :m], feats[i, 4:4 + m])
+    # shift by one frame: other half of the complex FFT, rounding-level agreement only
+    f1, l1 = layer(xc[:, shift:].contiguous(), lens - shift)
+    assert torch.equal(l1.cpu(), frames - 1)
+    diffs = []
+    for i in range(B):
+        m = int(frames[i]) - 1
+        diffs.append((f1[i, :m] - feats[i, 1:1 + m]).abs().flatten())
+    d = torch.cat(diffs)
+    # fp32 rounding only; the handful of ill-conditioned elements (DESIGN.md section 2) reach a few 1e-3
+    assert d.max().item() < 1e-2 and d.mean().item() < 1e-5 and (d > 1e-3).float().mean().item() < 1e-4, \
+        (d.max().item(), d.mean().item())
+
+
+def test_pinned_collator_int16_and_fp32(wavs):
+    """Row f4: pad into pinned staging, asynchronous H2D on a side stream, then SPLayer.forward --
+    identical features for the int16 and the fp32 staging paths and for the plain padded batch."""
+    from openasr_b200.batching import PinnedWaveCollator
+    layer, conf = make_layer()
+    layer.eval()
+    ws16 = [w.numpy().astype(np.int16) for w in (wavs[0], wavs[1], wavs[0][:30000])]
+    x, lens = pad_batch([torch.from_numpy(w.astype(np.float32)) for w in ws16])
+    ref, rlen = layer(x.cuda(), lens)
+    for int16 in (True, False):
+        col = PinnedWaveCollator("cuda:0", max_batch=4, max_len=max(lens) + 100, slots=2, int16=int16)
+        for _ in range(3):  # cycles through the slots (reuse after completion)
+            dev, l, ev = col(ws16)
+            col.wait(ev, dev)
+            f, fl = layer(dev, l)
+            assert dev.dtype == (torch.int16 if int16 else torch.float32)
+            assert torch.equal(fl, rlen) and torch.equal(f, ref)
