@@ -231,6 +231,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        from openasr_b200.batching import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)  # pinned staging buffers land on the GPU's NUMA node
     wl = args.workload
     B, lo, hi, sr, D, cmvn, sa = WORKLOADS[wl]
     conf = workload_config(wl, args.dither)
@@ -341,7 +345,8 @@ def run_ours(args):
         "config": {"workload": wl, "batch": B, "sample_rate": sr, "num_mel_bins": D, "cmvn": cmvn, "spec_aug": sa,
                    "dither": args.dither, "dither_rng": "device", "training": True,
                    "pool_batches": len(items), "pool_bytes": pool_bytes, "l2_flush": "pool larger than L2 (126 MB)",
-                   "cuda_graph_chunk": args.graph_chunk, "batches_in_flight": args.streams, "timing": "best of %d regions of K steps, CUDA events" % args.repeats, "partition": "by utterance, %d rank(s), no data-path collective" % world},
+                   "cuda_graph_chunk": args.graph_chunk, "batches_in_flight": args.streams, "timing": "best of %d regions of K steps, CUDA events" % args.repeats, "partition": "by utterance, %d rank(s), no data-path collective" % world,
+                   "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_int16_ingest": e2e_i16,
         "gpu_launches": lps * K, "clocks": clocks,
     }
@@ -438,6 +443,7 @@ def main():
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--graph-chunk", type=int, default=64)
     ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--streams", type=int, default=4, help="independent batches in flight inside the graph")
     ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -86,6 +86,27 @@ class BucketedTimeSampler(TimeBasedSampler):
         return 1.0 - used / padded if padded else 0.0
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU, so that pinned staging
+    buffers allocated afterwards are first-touched on the GPU's NUMA node and H2D / D2H DMA does not
+    cross the socket interconnect (matters once several ranks stage batches concurrently).
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (no error)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def pad_wave_batch(waveforms: Sequence[np.ndarray], out: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     """``load_wave_batch`` (data_utils.py:126-138) without the file IO: zero-pad 1-D waveforms to
