@@ -461,3 +461,38 @@ def test_pinned_collator_int16_and_fp32(wavs):
             f, fl = layer(dev, l)
             assert dev.dtype == (torch.int16 if int16 else torch.float32)
             assert torch.equal(fl, rlen) and torch.equal(f, ref)
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_fuzz_configs_vs_oracle(seed):
+    """Randomised geometry: batch size, ragged lengths down to a single window (1-, 2-, 3-frame groups and
+    utterances), odd row pitch and storage offset (unaligned TMA heads), sample rate, mel count, energy
+    column, int16 / fp32 ingest -- each against the CPU oracle, dither 0."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    sr = [16000, 8000][int(torch.randint(0, 2, (1,), generator=g))]
+    win = 400 if sr == 16000 else 200
+    D = [23, 40, 64, 80, 128][int(torch.randint(0, 5, (1,), generator=g))]
+    B = int(torch.randint(1, 24, (1,), generator=g))
+    use_energy = bool(torch.randint(0, 2, (1,), generator=g))
+    as_int16 = bool(torch.randint(0, 2, (1,), generator=g))
+    hi = [win + 3, win + 700, 9000, 30000][int(torch.randint(0, 4, (1,), generator=g))]
+    lens = torch.randint(win, hi + 1, (B,), generator=g)
+    pitch = int(lens.max()) + int(torch.randint(0, 7, (1,), generator=g))
+    off = int(torch.randint(0, 4, (1,), generator=g))
+    x = (1500.0 * torch.randn(B, pitch, generator=g)).round().clamp(-32768, 32767)
+    x = x * (torch.arange(pitch)[None, :] < lens[:, None])
+    layer, conf = make_layer(sample_rate=sr, num_mel_bins=D, use_energy=use_energy)
+    layer.eval()
+    store = torch.zeros(B * pitch + off)
+    store[off:] = x.flatten()
+    xd = store.cuda()[off:].view(B, pitch)  # storage offset: rows start at 4-byte, not 16-byte, boundaries
+    if as_int16:
+        xd = xd.to(torch.int16)
+    feats, flen = layer(xd, lens)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
+    ref64, _ = fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)
+    assert torch.equal(flen.cpu(), rlen)
+    assert feats.shape == ref.shape
+    close(feats, ref, ref64)
+    for i in range(B):
+        assert (feats[i, int(rlen[i]):] == 0).all()
