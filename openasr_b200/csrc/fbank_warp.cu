@@ -1,19 +1,24 @@
-// Kernel A (warp-pipelined): fused frame -> (dither) -> DC removal -> pre-emphasis -> window ->
-// real FFT -> power -> sparse mel -> log, one CTA of 16 *independent* warps per SM.
+// Kernel A (warp-pipelined, default): fused frame -> (dither) -> DC removal -> pre-emphasis -> window ->
+// real FFT -> power -> sparse mel -> log, two CTAs of 8 *independent* warps per SM.
 //
 // Replaces src/third_party/kaldi_signal.py:163-211 + :510-552 and the pad/stack loop of
-// src/blocks/sp_layers.py:81-91.  Same arithmetic as fbank_kernel.cu / fbank_persistent.cu;
-// what changes is the execution structure, driven by the ncu profiles under profiles/:
+// src/blocks/sp_layers.py:81-91.  Execution structure, driven by the ncu profiles and the clock64
+// timelines under profiles/:
 //   * the unit of work is a GROUP of <= 4 consecutive frames of one utterance, processed end to
 //     end by ONE warp: TMA bulk copy of the group's samples -> two packed complex FFTs ->
 //     power rows -> mel (lane = frame x filter slice) -> log -> coalesced store.  Inside the main
 //     loop there is no __syncthreads: warps never wait for each other, only for their own TMA;
-//   * every CTA owns an equal, contiguous share of the batch's group list and its warps pull
-//     groups from a shared-memory counter, so the load balance is at 4-frame granularity;
+//   * all floating-point work runs on Blackwell's packed fp32 pipe (fft_c2.cuh: FADD2 / FMUL2 /
+//     FFMA2): frames (t, t+1) are the (re, im) halves of one 64-bit register pair from the first
+//     sample load on, so framing, butterflies, twiddles and power cost one instruction per pair;
+//   * every CTA owns an equal, contiguous share of the batch's group list (the two CTAs that share an
+//     SM get consecutive shares); warp w starts on group g0 + w, later groups come from a
+//     shared-memory counter, so the load balance is at 4-frame granularity;
 //   * the sample buffer aliases the second pair's exchange planes (dead until the stage-1 output
 //     of that pair is written), so the next group's samples land behind FFT stage 2 / mel / store;
-//   * per-utterance CMVN sums are kept in registers, merged per CTA in shared memory and flushed
-//     with one fp64 atomic per (utterance, column) per CTA.
+//   * per-utterance CMVN sums are kept per warp in fp64 shared-memory rows and merged per CTA after
+//     the loop, one fp64 global atomic per (utterance, column) per CTA; the batch's zero-padding
+//     rows are written by each warp after its last group.
 #include "fbank_frame.cuh"
 
 namespace spl {
