@@ -35,7 +35,7 @@ import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of fbank_warp_kernel per launch (ncu --set full,
 # profiles/r1_summary.md); the feature writes are still L2-resident when the kernel retires
-NCU_TRAFFIC = {"aishell": 10.22e6}
+NCU_TRAFFIC = {"aishell": 9.88e6}  # prof_w5_d1: 9.878 MB read + 0 written (features leave L2 after the launch)
 
 WORKLOADS = {
     # name: (B, n_lo, n_hi, sample_rate, D, cmvn, spec_aug)
@@ -322,7 +322,7 @@ def run_ours(args):
     alg_bytes = sum(items[i % len(items)]["alg_bytes"] for i in range(K)) / K
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (ms_a * 1e-3 / K) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fbank_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "fbank_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(wl), "peak_source": peak_src,
                 "us_per_launch": 1e3 * ms_a / K, "alg_bytes_per_launch": alg_bytes,
                 "step_share": ms_a / ms_total if world == 1 else None}
