@@ -496,3 +496,31 @@ def test_fuzz_configs_vs_oracle(seed):
     close(feats, ref, ref64)
     for i in range(B):
         assert (feats[i, int(rlen[i]):] == 0).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_dataparallel_two_gpus(wavs):
+    """train.py:134 wraps the model in torch.nn.DataParallel: SPLayer replicas run concurrently in per-GPU
+    threads (shared Python attributes, one handle per device)."""
+    from openasr_b200 import SPLayer
+
+    class Model(torch.nn.Module):
+        def __init__(self, conf):
+            super().__init__()
+            self.splayer = SPLayer(conf)
+
+        def forward(self, wav, lens):
+            feats, flen = self.splayer(wav, lens)
+            return feats, flen
+
+    conf = {"feature_type": "fbank", "sample_rate": 16000, "num_mel_bins": 80, "use_energy": False, "dither": 0.0,
+            "cmvn": "utterance"}
+    ws = [wavs[0], wavs[1][:wavs[0].shape[0]], wavs[0].flip(0), wavs[1][1000:1000 + wavs[0].shape[0]]]
+    x, lens = pad_batch(ws)  # equal lengths: DataParallel's gather needs the same T on every replica
+    model = torch.nn.DataParallel(Model(conf).cuda().eval(), device_ids=[0, 1])
+    single = SPLayer(conf).cuda().eval()
+    ref, rlen = single(x.cuda(), lens)
+    for _ in range(5):
+        feats, flen = model(x.cuda(), torch.tensor(lens).cuda())
+        assert torch.equal(flen.cpu(), rlen.cpu())
+        assert torch.equal(feats.cpu(), ref.cpu())
