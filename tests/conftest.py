@@ -12,6 +12,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built extension (the .so is git-ignored): build it once, like the driver does
+    lib = os.path.join(ROOT, "openasr_b200", "lib", "libspl_b200.so")
+    if not os.path.isfile(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):
