@@ -432,12 +432,93 @@ def run_cpu_baseline(conf, items, sr):
             "sample": "%d of %d utterances of one batch (%.1f audio-s), best of 2 after 1 warm-up utterance" % (n, len(lens), audio)}
 
 
+def run_conv0(args):
+    """Row f2 (conv0 + ReLU on the front-end's features), same rules as the main arm: CUDA events,
+    >= 3 warm-ups, outputs cycled over a pool larger than L2, one JSON line.  `value` = audio-seconds/s
+    through the layer at the AISHELL shape; roofline = HBM (the layer writes C*D1/(2D) = 15.6x its
+    input); `library` = the same op through torch / cuDNN; `cpu_baseline` = the oracle port."""
+    import ctypes as Ct
+    from openasr_b200 import _capi
+    dev = torch.device("cuda", 0)
+    B, T, D, C = 32, 649, 80, 32
+    audio_s = 32 * 5.0  # the AISHELL batch these features come from (mean 5 s per utterance)
+    gen = torch.Generator().manual_seed(0)
+    x = (4.0 * torch.randn(B, T, D, generator=gen) + 8.0).to(dev)
+    w = (0.3 * torch.randn(C, 1, 3, 3, generator=gen)).to(dev)
+    b = (0.1 * torch.randn(C, generator=gen)).to(dev)
+    T1, D1 = (T - 3) // 2 + 1, D - 2
+    alg_bytes = 4 * B * T * D + 4 * B * C * T1 * D1
+    lib = _capi.load()
+    outs = [torch.empty((B, C, T1, D1), device=dev) for _ in range(3)]  # 3 x 103 MB > L2
+    stream = torch.cuda.Stream(device=dev)
+
+    def ours(i):
+        o = outs[i % len(outs)]
+        _capi.check(lib.spl_conv0_relu(None, Ct.c_void_p(x.data_ptr()), B, T, D, Ct.c_void_p(w.data_ptr()),
+                                       Ct.c_void_p(b.data_ptr()), C, Ct.c_void_p(o.data_ptr()),
+                                       Ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
+    def library(i):
+        torch.relu_(torch.nn.functional.conv2d(x.unsqueeze(1), w, b, stride=(2, 1)))
+
+    def timed(fn, K):
+        with torch.cuda.stream(stream):
+            for i in range(max(3, args.warmup)):
+                fn(i)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(K):
+                    fn(i)
+            g.replay()
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = None
+            for _ in range(args.repeats):
+                e0.record(stream)
+                g.replay()
+                e1.record(stream)
+                stream.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+        return 1e3 * best / K  # us per launch
+
+    K = max(8, min(args.steps, 64))
+    launches0 = _capi.launch_count()
+    us_ours = timed(ours, K)
+    n_launch = _capi.launch_count() - launches0
+    us_lib = timed(library, K)
+    peak, src = measured_peaks()
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import conv_oracle as co
+        xc, wc, bc = x.cpu(), w.cpu(), b.cpu()
+        torch.set_num_threads(os.cpu_count() or 1)
+        co.conv0_relu(xc, wc, bc)
+        t0 = time.perf_counter()
+        co.conv0_relu(xc, wc, bc)
+        cpu = {"value": audio_s / (time.perf_counter() - t0), "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "the whole batch once after one warm-up"}
+    print(json.dumps({
+        "metric": "audio-sec/sec through conv0+ReLU (row f2)", "value": audio_s / (us_ours * 1e-6), "unit": "audio-s/s",
+        "n_gpus": 1, "steps": K, "warmup": max(3, args.warmup), "ms_per_step": us_ours * 1e-3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "aishell features 32x649x80 -> 32x32x324x78", "pool": "3 outputs of 103 MB (> L2)"},
+        "roofline": {"bound": "hbm", "kernel": "conv0_relu_kernel", "achieved": alg_bytes / (us_ours * 1e-6) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": alg_bytes / (us_ours * 1e-6) / 1e9 / peak, "traffic": None,
+                     "alg_bytes_per_launch": alg_bytes, "peak_source": src, "us_per_launch": us_ours},
+        "library": {"impl": "torch conv2d + relu_ (cuDNN)", "us_per_launch": us_lib},
+        "cpu_baseline": cpu, "gpu_launches": int(n_launch)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=640)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--stage", default="frontend", choices=["frontend", "conv0"],
+                    help="frontend: the SPLayer hot path (default, the contract line); conv0: row f2 on its features")
     ap.add_argument("--workload", default="aishell", choices=sorted(WORKLOADS))
     ap.add_argument("--dither", type=float, default=1.0)
     ap.add_argument("--pool", type=int, default=16)
@@ -448,6 +529,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.stage == "conv0" and args.impl == "ours":
+        run_conv0(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

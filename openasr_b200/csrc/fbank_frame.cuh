@@ -222,8 +222,8 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
             float csA, csB;
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csA) : "f"(c2_re(ang)));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csB) : "f"(c2_im(ang)));
-            const c2 g = c2_mul(c2_make(fast_sqrt(c2_re(a)), fast_sqrt(c2_im(a))), c2_make(csA * sgn, csB * sgn));
-            if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = x[n1] + g;
+            const c2 g = c2_mul(c2_make(fast_sqrt(c2_re(a)), fast_sqrt(c2_im(a))), c2_make(csA, csB));
+            if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = c2_fma(g, c2_splat(sgn), x[n1]);  // sign of `dither`
           }
         }
       }
