@@ -524,3 +524,37 @@ def test_dataparallel_two_gpus(wavs):
         feats, flen = model(x.cuda(), torch.tensor(lens).cuda())
         assert torch.equal(flen.cpu(), rlen.cpu())
         assert torch.equal(feats.cpu(), ref.cpu())
+
+
+@pytest.mark.parametrize("sr", [6000, 10000, 11025, 12000, 20000])
+def test_other_sample_rates_generic_window(sr, monkeypatch):
+    """Sample rates whose window is not the 400 / 200-sample special case run the generic-window
+    instantiations (dynamic row validity, 16 un-pruned FFT rows) of every kernel-A engine."""
+    S, Nw, Nfft = fo.frame_params(float(sr))
+    assert Nfft in (256, 512)
+    g = torch.Generator().manual_seed(sr)
+    B = 7
+    lens = torch.randint(Nw, 6 * sr // 10, (B,), generator=g)
+    lens[0] = Nw  # exactly one frame
+    x = (1800.0 * torch.randn(B, int(lens.max()), generator=g)).round()
+    x = x * (torch.arange(x.shape[1])[None, :] < lens[:, None])
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("SPL_LEGACY_KERNEL", mode)
+        layer, conf = make_layer(sample_rate=sr, num_mel_bins=40, use_energy=True)
+        layer.eval()
+        outs[mode], flen = layer(x.cuda(), lens)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
+    ref64, _ = fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)
+    assert torch.equal(flen.cpu(), rlen)
+    for mode in outs:
+        close(outs[mode], ref, ref64)
+    # host-stream dither (parity mode) on the generic path
+    monkeypatch.setenv("SPL_LEGACY_KERNEL", "0")
+    layer, conf = make_layer(sample_rate=sr, num_mel_bins=40, dither=1.0, dither_rng="host")
+    layer.eval()
+    torch.manual_seed(5)
+    f, _ = layer(x[:3].cuda(), lens[:3])
+    torch.manual_seed(5)
+    r, _ = fo.splayer_forward(x[:3], lens[:3].tolist(), conf)
+    close(f, r)
