@@ -174,8 +174,9 @@ __device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& 
 // j = R2 n1 + n2 after dither -> DC removal -> (raw log-energy) -> pre-emphasis -> window
 // (kaldi_signal.py:174-199).  Frame A becomes the real part and frame B the imaginary part of the
 // complex FFT input, so every arithmetic step is one fp32x2 instruction for both frames.
-template <int NFFT, int NW, bool NOISE>
-__device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& p, const float* frA, const float* frB,
+// ST: element type of the staged samples (float, or int16_t PCM converted at the first register load).
+template <int NFFT, int NW, bool NOISE, typename ST>
+__device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& p, const ST* frA, const ST* frB,
                                                 const float* win, float* energy_slots /*[2]*/, int n2, int b, int tA,
                                                 int tB, bool validA, bool validB) {
   using G = Geo<NFFT>;
@@ -185,7 +186,7 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
 #pragma unroll
   for (int n1 = 0; n1 < F::NROW; ++n1) {
     const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
-    x[n1] = c2_make(rv ? frA[G::R2 * n1 + n2] : 0.f, rv ? frB[G::R2 * n1 + n2] : 0.f);
+    x[n1] = c2_make(rv ? (float)frA[G::R2 * n1 + n2] : 0.f, rv ? (float)frB[G::R2 * n1 + n2] : 0.f);
   }
   if constexpr (NOISE) {
     if (p.noise != nullptr) {  // parity mode: host-drawn rand_gauss, [B, T, Nw]
@@ -267,7 +268,7 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
     } else {
       const int j = G::R2 * n1 + n2;
       const int jp = (row_valid<NFFT, NW>(n1, n2, Nw) ? j : 1) - 1;
-      prev = (n1 == 0 && n2 == 0) ? x[0] : c2_make(frA[jp], frB[jp]);
+      prev = (n1 == 0 && n2 == 0) ? x[0] : c2_make((float)frA[jp], (float)frB[jp]);
     }
     const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
     const float wj = rv ? win[G::R2 * n1 + n2] : 0.f;

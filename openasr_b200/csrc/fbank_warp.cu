@@ -5,7 +5,7 @@
 // src/blocks/sp_layers.py:81-91.  Execution structure, driven by the ncu profiles and the clock64
 // timelines under profiles/:
 //   * the unit of work is a GROUP of <= 4 consecutive frames of one utterance, processed end to
-//     end by ONE warp: TMA bulk copy of the group's samples -> two packed complex FFTs ->
+//     end by ONE warp: TMA bulk copy of the group's samples (fp32 or raw int16 PCM) -> two packed complex FFTs ->
 //     power rows -> mel (lane = frame x filter slice) -> log -> coalesced store.  Inside the main
 //     loop there is no __syncthreads: warps never wait for each other, only for their own TMA;
 //   * all floating-point work runs on Blackwell's packed fp32 pipe (fft_c2.cuh: FADD2 / FMUL2 /
@@ -80,7 +80,9 @@ size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NFFT, int NW, bool NOISE>
+// ST = element type of the input samples: float (int16-scaled) or int16_t PCM (row f1); both are staged
+// by TMA as raw bytes and converted when the frames are loaded into registers.
+template <int NFFT, int NW, bool NOISE, typename ST>
 __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankParams p) {
   using G = Geo<NFFT>;
   using F = FG<NFFT, NW>;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   float* wr = smem + L.off_warp + w * L.rw;  // this warp's region
   float* e0 = wr;                            // pair 0 exchange: re plane, im plane at + PL ; power rows alias it
   float* e1 = wr + L.p1;                     // pair 1 exchange ; the sample buffer aliases it
-  float* samp = e1;
+  ST* samp = reinterpret_cast<ST*>(e1);
   float* orows = wr + L.out_off;
   float* energy = wr + L.en_off;
   double* wstat = reinterpret_cast<double*>(wr + L.st_off);  // fp64: sum x^2 - mean^2 must survive std << mean
@@ -205,8 +207,8 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
 
   // ---- per-warp helpers ---------------------------------------------------------------------------
   const char* wav_lo = static_cast<const char*>(p.wav);
-  const size_t esz = p.sample_format == SPL_SAMPLES_F32 ? 4 : 2;
-  const char* wav_hi = wav_lo + ((size_t)(B - 1) * p.wav_pitch + (size_t)p.wav_cols) * esz;
+  constexpr int ES = (int)sizeof(ST);
+  const char* wav_hi = wav_lo + ((size_t)(B - 1) * p.wav_pitch + (size_t)p.wav_cols) * ES;
   int b_hint = b_first;
   auto fetch_group = [&]() {  // warp-uniform: next group id of this CTA (or >= g1)
     int g = 0;
@@ -229,11 +231,11 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
     const int need = (q.n - 1) * S + Nw;
     q.bulk = false;
     q.head = 0;
-    if (p.sample_format == SPL_SAMPLES_F32) {
-      const char* src = wav_lo + ((size_t)b * p.wav_pitch + (size_t)q.t0 * S) * 4;
+    {
+      const char* src = wav_lo + ((size_t)b * p.wav_pitch + (size_t)q.t0 * S) * ES;
       const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
-      const int head = (int)((src - a0) >> 2);
-      const uint32_t bytes = (uint32_t)(((head + need) * 4 + 15) & ~15);
+      const int head = (int)((src - a0) / ES);  // 0..3 floats or 0..7 int16 before the first sample
+      const uint32_t bytes = (uint32_t)(((head + need) * ES + 15) & ~15);
       if (a0 >= wav_lo && a0 + bytes <= wav_hi) {
         q.bulk = true;
         q.head = head;
@@ -288,20 +290,14 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       mbar_wait(mybar, parity);
       parity ^= 1;
       TR(5 + 6 * tr_it);
-    } else {  // scalar staging (int16 ingest, unaligned or boundary windows)
-      const size_t gofs = (size_t)cur.b * p.wav_pitch + (size_t)cur.t0 * S;
-      if (p.sample_format == SPL_SAMPLES_F32) {
-        const float* src = static_cast<const float*>(p.wav) + gofs;
-        for (int i = lane; i < need; i += 32) samp[i] = __ldg(src + i);
-      } else {
-        const int16_t* src = static_cast<const int16_t*>(p.wav) + gofs;
-        for (int i = lane; i < need; i += 32) samp[i] = (float)__ldg(src + i);
-      }
+    } else {  // warp-load staging (windows whose 16-byte envelope would leave the batch buffer)
+      const ST* src = static_cast<const ST*>(p.wav) + (size_t)cur.b * p.wav_pitch + (size_t)cur.t0 * S;
+      for (int i = lane; i < need; i += 32) samp[i] = __ldg(src + i);
       __syncwarp();
     }
-    const float* sbase = samp + cur.head;
+    const ST* sbase = samp + cur.head;
     if (n < 4) {  // invalid frames must read finite data: zero everything past the valid span
-      for (int i = need + lane; i < 3 * S + Nw; i += 32) samp[cur.head + i] = 0.f;
+      for (int i = need + lane; i < 3 * S + Nw; i += 32) samp[cur.head + i] = (ST)0;
       __syncwarp();
     }
 
@@ -317,7 +313,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
         twi[k1] = tws[NFFT + k1 * G::R2 + n2];
       }
       c2 z0[16], z1[16];
-      load_frame_pair<NFFT, NW, NOISE>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0, cur.t0 + 1, true,
+      load_frame_pair<NFFT, NW, NOISE, ST>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0, cur.t0 + 1, true,
                                        n > 1);
       fft_dif_c<16, F::NROW>(z0);
       {
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
           ei[k1] = c2_im(o);
         }
       }
-      load_frame_pair<NFFT, NW, NOISE>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b, cur.t0 + 2,
+      load_frame_pair<NFFT, NW, NOISE, ST>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b, cur.t0 + 2,
                                        cur.t0 + 3, n > 2, n > 3);
       __syncwarp();  // every lane has its samples in registers: pair 1's planes may overwrite the buffer
       fft_dif_c<16, F::NROW>(z1);
@@ -348,7 +344,7 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
       const int pr = lane >> 4, n2 = lane & 15;
       const int fa = 2 * pr;
       c2 z[16];
-      load_frame_pair<NFFT, NW, NOISE>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
+      load_frame_pair<NFFT, NW, NOISE, ST>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
                                        cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n);
       __syncwarp();  // samples are in registers; pair 1's planes alias the buffer
       fft_dif_c<16, F::NROW>(z);
@@ -585,29 +581,35 @@ extern "C" __attribute__((visibility("default"))) int spl_debug_trace(unsigned l
 #endif
 
 // ---------------------------------------------------------------------------------------------
-template <int NFFT, int NW, bool NOISE>
+template <int NFFT, int NW, bool NOISE, typename ST>
 static cudaError_t launch_w(const FbankParams& p, int num_ctas, cudaStream_t st) {
   const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out, p.tab.wtab_words);
   static thread_local size_t configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 16 || configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(fbank_warp_kernel<NFFT, NW, NOISE>,
+    cudaError_t e = cudaFuncSetAttribute(fbank_warp_kernel<NFFT, NW, NOISE, ST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = smem;
   }
-  fbank_warp_kernel<NFFT, NW, NOISE><<<num_ctas, kWThreads, smem, st>>>(p);
+  fbank_warp_kernel<NFFT, NW, NOISE, ST><<<num_ctas, kWThreads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int NFFT, int NW, bool NOISE>
+static cudaError_t launch_fmt(const FbankParams& p, int num_ctas, cudaStream_t st) {
+  return p.sample_format == SPL_SAMPLES_F32 ? launch_w<NFFT, NW, NOISE, float>(p, num_ctas, st)
+                                            : launch_w<NFFT, NW, NOISE, int16_t>(p, num_ctas, st);
 }
 
 cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st) {
   if (nfft == 512) {
-    if (p.Nw == 400) return with_noise ? launch_w<512, 400, true>(p, num_ctas, st) : launch_w<512, 400, false>(p, num_ctas, st);
-    return with_noise ? launch_w<512, 0, true>(p, num_ctas, st) : launch_w<512, 0, false>(p, num_ctas, st);
+    if (p.Nw == 400) return with_noise ? launch_fmt<512, 400, true>(p, num_ctas, st) : launch_fmt<512, 400, false>(p, num_ctas, st);
+    return with_noise ? launch_fmt<512, 0, true>(p, num_ctas, st) : launch_fmt<512, 0, false>(p, num_ctas, st);
   }
-  if (p.Nw == 200) return with_noise ? launch_w<256, 200, true>(p, num_ctas, st) : launch_w<256, 200, false>(p, num_ctas, st);
-  return with_noise ? launch_w<256, 0, true>(p, num_ctas, st) : launch_w<256, 0, false>(p, num_ctas, st);
+  if (p.Nw == 200) return with_noise ? launch_fmt<256, 200, true>(p, num_ctas, st) : launch_fmt<256, 200, false>(p, num_ctas, st);
+  return with_noise ? launch_fmt<256, 0, true>(p, num_ctas, st) : launch_fmt<256, 0, false>(p, num_ctas, st);
 }
 
 }  // namespace spl
