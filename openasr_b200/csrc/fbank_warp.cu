@@ -24,10 +24,10 @@
 namespace spl {
 
 #ifdef SPL_TRACE  // per-warp clock64 timeline (tools/trace_warp.py); never defined in the shipped library
-__device__ unsigned long long g_trace[296 * 8 * 32];
+__device__ unsigned long long g_trace[296 * 8 * 32];  // [CTA][warp][slot], CTA stride = warps per CTA
 #define TR(slot)                                                                                   \
   do {                                                                                             \
-    if (lane == 0 && (slot) < 32) g_trace[((size_t)blockIdx.x * 8 + w) * 32 + (slot)] = clock64(); \
+    if (lane == 0 && (slot) < 32) g_trace[((size_t)blockIdx.x * (blockDim.x >> 5) + w) * 32 + (slot)] = clock64(); \
   } while (0)
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -38,8 +38,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TR(slot) do { } while (0)
 #endif
 
-constexpr int kWWarps = 8;   // two such CTAs per SM: 16 resident warps (register-file bound at 128 regs)
-constexpr int kWThreads = kWWarps * 32;
+// Resident warps per SM are register-file bound (128 regs x 16 warps).  Default: ONE CTA of 16 warps per SM,
+// so that all 16 warps pull groups from one counter (two 8-warp CTAs per SM finish 20 % apart: the warps of the
+// CTA that was placed first win the issue arbitration, profiles/r1_summary.md).  The 8-warp variant is the
+// throughput mode (SPL_CTAS_PER_SM=1: two different launches co-resident on every SM).
+constexpr int kWMaxWarps = 16;
 
 struct WLayout {
   int pair;      // floats of one pair's exchange area (re plane + im plane)
@@ -52,7 +55,7 @@ struct WLayout {
   int off_tab, off_gpre, off_fpre, off_ctl, off_bar, off_warp, total;
 };
 
-__host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words) {
+__host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words, int warps) {
   WLayout L;
   const int pl = nfft == 512 ? Geo<512>::PL : Geo<256>::PL;
   L.pair = 2 * pl;
@@ -67,28 +70,29 @@ __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_o
   L.off_gpre = wtab_words;
   L.off_fpre = L.off_gpre + kMaxPersistentB + 1;
   L.off_ctl = (L.off_fpre + kMaxPersistentB + 1 + 3) & ~3;
-  L.off_bar = (L.off_ctl + 8 + kWWarps + 1) & ~1;  // ctl[8] + last utterance of every warp
-  L.off_warp = (L.off_bar + 2 * (kWWarps + 1) + 31) & ~31;
-  L.total = L.off_warp + kWWarps * L.rw;
+  L.off_bar = (L.off_ctl + 8 + warps + 1) & ~1;  // ctl[8] + last utterance of every warp
+  L.off_warp = (L.off_bar + 2 * (warps + 1) + 31) & ~31;
+  L.total = L.off_warp + warps * L.rw;
   (void)S;
   (void)Nw;
   return L;
 }
 
-size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words) {
-  return sizeof(float) * (size_t)make_wlayout(nfft, S, Nw, D_out, wtab_words).total;
+size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words, int warps) {
+  return sizeof(float) * (size_t)make_wlayout(nfft, S, Nw, D_out, wtab_words, warps).total;
 }
 
 // ---------------------------------------------------------------------------------------------
 // ST = element type of the input samples: float (int16-scaled) or int16_t PCM (row f1); both are staged
 // by TMA as raw bytes and converted when the frames are loaded into registers.
-template <int NFFT, int NW, bool NOISE, typename ST>
-__global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankParams p) {
+template <int NFFT, int NW, bool NOISE, typename ST, int kWWarps>
+__global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(const FbankParams p) {
+  constexpr int kWThreads = kWWarps * 32;
   using G = Geo<NFFT>;
   using F = FG<NFFT, NW>;
   extern __shared__ __align__(128) float smem[];
   const int S = p.S, Nw = F::kStatic ? NW : p.Nw, D_out = p.D_out;
-  const WLayout L = make_wlayout(NFFT, S, Nw, D_out, p.tab.wtab_words);
+  const WLayout L = make_wlayout(NFFT, S, Nw, D_out, p.tab.wtab_words, kWWarps);
   static_assert(2 * G::PL >= 4 * G::PP, "power rows must fit in pair 0's exchange area");
   float* tab = smem + L.off_tab;
   const float4* melw = reinterpret_cast<const float4*>(tab);
@@ -106,10 +110,10 @@ __global__ void __launch_bounds__(kWThreads, 2) fbank_warp_kernel(const FbankPar
   TR(0);
 #ifdef SPL_TRACE
   if (lane == 0) {
-    g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 1] = gtimer();
+    g_trace[((size_t)blockIdx.x * (blockDim.x >> 5) + w) * 32 + 1] = gtimer();
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g_trace[((size_t)blockIdx.x * 8 + w) * 32 + 26] = smid;
+    g_trace[((size_t)blockIdx.x * (blockDim.x >> 5) + w) * 32 + 26] = smid;
   }
   int tr_it = 0;
 #endif
@@ -581,35 +585,41 @@ extern "C" __attribute__((visibility("default"))) int spl_debug_trace(unsigned l
 #endif
 
 // ---------------------------------------------------------------------------------------------
-template <int NFFT, int NW, bool NOISE, typename ST>
+template <int NFFT, int NW, bool NOISE, typename ST, int WARPS>
 static cudaError_t launch_w(const FbankParams& p, int num_ctas, cudaStream_t st) {
-  const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out, p.tab.wtab_words);
+  const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out, p.tab.wtab_words, WARPS);
   static thread_local size_t configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 16 || configured[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(fbank_warp_kernel<NFFT, NW, NOISE, ST>,
+    cudaError_t e = cudaFuncSetAttribute(fbank_warp_kernel<NFFT, NW, NOISE, ST, WARPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = smem;
   }
-  fbank_warp_kernel<NFFT, NW, NOISE, ST><<<num_ctas, kWThreads, smem, st>>>(p);
+  fbank_warp_kernel<NFFT, NW, NOISE, ST, WARPS><<<num_ctas, WARPS * 32, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 template <int NFFT, int NW, bool NOISE>
-static cudaError_t launch_fmt(const FbankParams& p, int num_ctas, cudaStream_t st) {
-  return p.sample_format == SPL_SAMPLES_F32 ? launch_w<NFFT, NW, NOISE, float>(p, num_ctas, st)
-                                            : launch_w<NFFT, NW, NOISE, int16_t>(p, num_ctas, st);
+static cudaError_t launch_fmt(const FbankParams& p, int warps, int num_ctas, cudaStream_t st) {
+  if (warps == 16)
+    return p.sample_format == SPL_SAMPLES_F32 ? launch_w<NFFT, NW, NOISE, float, 16>(p, num_ctas, st)
+                                              : launch_w<NFFT, NW, NOISE, int16_t, 16>(p, num_ctas, st);
+  return p.sample_format == SPL_SAMPLES_F32 ? launch_w<NFFT, NW, NOISE, float, 8>(p, num_ctas, st)
+                                            : launch_w<NFFT, NW, NOISE, int16_t, 8>(p, num_ctas, st);
 }
 
-cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st) {
+// warps: 16 (one CTA per SM, default) or 8 (throughput mode / shared-memory fallback)
+cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int warps, int num_ctas, cudaStream_t st) {
   if (nfft == 512) {
-    if (p.Nw == 400) return with_noise ? launch_fmt<512, 400, true>(p, num_ctas, st) : launch_fmt<512, 400, false>(p, num_ctas, st);
-    return with_noise ? launch_fmt<512, 0, true>(p, num_ctas, st) : launch_fmt<512, 0, false>(p, num_ctas, st);
+    if (p.Nw == 400)
+      return with_noise ? launch_fmt<512, 400, true>(p, warps, num_ctas, st) : launch_fmt<512, 400, false>(p, warps, num_ctas, st);
+    return with_noise ? launch_fmt<512, 0, true>(p, warps, num_ctas, st) : launch_fmt<512, 0, false>(p, warps, num_ctas, st);
   }
-  if (p.Nw == 200) return with_noise ? launch_fmt<256, 200, true>(p, num_ctas, st) : launch_fmt<256, 200, false>(p, num_ctas, st);
-  return with_noise ? launch_fmt<256, 0, true>(p, num_ctas, st) : launch_fmt<256, 0, false>(p, num_ctas, st);
+  if (p.Nw == 200)
+    return with_noise ? launch_fmt<256, 200, true>(p, warps, num_ctas, st) : launch_fmt<256, 200, false>(p, warps, num_ctas, st);
+  return with_noise ? launch_fmt<256, 0, true>(p, warps, num_ctas, st) : launch_fmt<256, 0, false>(p, warps, num_ctas, st);
 }
 
 }  // namespace spl

@@ -48,6 +48,7 @@ struct spl_handle {
   int num_sms;
   int kernel;  // 0 warp-pipelined (default), 1 simple one-tile-per-CTA (SPL_LEGACY_KERNEL=1), 2 persistent CTA tiles (=2)
   size_t smem_warp;
+  size_t smem_warp16;
   size_t smem_pair;
   int ctas_per_sm;
   void* blob;  // single device allocation holding every table
@@ -462,7 +463,8 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->ctas_per_sm = (cps && cps[0] == '1') ? 1 : 2;
   h->smem_pair = nfft == 512 ? spl::fbank_pair_smem_bytes(h->D_out, (int)qt_words) : 0;
   if (h->kernel == 4 && (nfft != 512 || h->smem_pair > 113 * 1024 || S + Nw + 4 > 564)) h->kernel = 0;
-  h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words);
+  h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 8);
+  h->smem_warp16 = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 16);
   {  // the warp kernel stages a group's samples inside one pair's exchange planes
     const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
     if (h->kernel == 0 && (h->smem_warp > 113 * 1024 || 3 * S + Nw + 4 > 2 * pl)) h->kernel = 2;
@@ -535,7 +537,13 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   else if (h->kernel == 4 && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_pair(p, with_noise, h->ctas_per_sm * h->num_sms, st);
   else if ((h->kernel == 0 || h->kernel == 3 || h->kernel == 4) && a->B <= spl::kMaxPersistentB)
-    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, h->ctas_per_sm * h->num_sms, st);
+    {
+    // default: one 16-warp CTA per SM; SPL_CTAS_PER_SM=1 (throughput mode) or a table block too large for
+    // 227 KB: 8-warp CTAs
+    const bool wide = h->ctas_per_sm == 2 && h->smem_warp16 <= 227 * 1024;
+    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, wide ? 16 : 8,
+                               wide ? h->num_sms : h->ctas_per_sm * h->num_sms, st);
+  }
   else if (h->kernel == 2 && a->B <= spl::kMaxPersistentB)
     e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
   else

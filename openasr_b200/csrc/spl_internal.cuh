@@ -104,8 +104,8 @@ constexpr int kMaxPersistentB = 512;
 cudaError_t launch_fbank_persistent(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
 size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_words);
 // warp-pipelined kernel: one CTA of 16 independent warps per SM, no block-wide barriers in the loop
-cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
-size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words);
+cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int warps, int num_ctas, cudaStream_t st);
+size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words, int warps);
 // pair-pipelined kernel (Nfft = 512 only): 2 CTAs x 12 warps per SM, one packed pair per warp iteration
 cudaError_t launch_fbank_pair(const FbankParams& p, bool with_noise, int num_ctas, cudaStream_t st);
 size_t fbank_pair_smem_bytes(int D_out, int qtab_words);
