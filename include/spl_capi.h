@@ -97,6 +97,13 @@ typedef struct spl_fbank_args {
 
 SPL_API int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream /* cudaStream_t */);
 
+/* Several padded batches in ONE persistent launch of kernel A (the per-utterance loop of sp_layers.py:81-91
+ * over a queue of batches): `args[0..n)` as for spl_fbank_forward; every batch has its own buffers, lengths
+ * and T.  Launch, prologue and tail are paid once, and the frames of all batches are balanced over the SMs
+ * together.  Up to 8 batches / 512 utterances share a launch; larger calls are split transparently.
+ * dither_seed and global_stats are taken from the first batch of each launch. */
+SPL_API int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n, void* stream);
+
 /* CMVN + SpecAug in place on [B, T, Dm] (kernel B).  Closed form of sp_layers.py:51-74:
  * time-masked -> time mean of the (normalised, un-masked) features; else freq-masked ->
  * per-frame mean over Dm; else the (normalised) value.  Rows t >= feat_len stay 0 except
@@ -147,6 +154,19 @@ SPL_API int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N,
                             void* stream);
 
 /* Introspection */
+/* kernel-A engine a call with this sample format runs on: "umma" (tcgen05 DFT-as-GEMM), "fft", "simple" */
+SPL_API const char* spl_engine_name(const spl_handle* h, int32_t sample_format);
+/* Host-only (no device needed): the tcgen05 engine's tables for a configuration, for the CPU model of the kernel
+ * in tests/ (tools/emulate_umma.py).  fmt 0 = fp32 samples, 1 = int16.  info[6] = {supported, twiddle bytes, table
+ * floats, offset of the mel weights, offset of the shift codes, trailing emits}.  Buffers may be NULL to query sizes. */
+SPL_API int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* window, const float* mel_dense,
+                                  int32_t fmt, void* twiddles, size_t twiddle_cap, float* tab, size_t tab_cap,
+                                  int32_t* info);
+/* SYNCHRONOUS diagnostics: raw tcgen05 accumulators [128][4*Nfft/4 + 1] of the first tile (handle created with
+ * SPL_UMMA_DEBUG=1 in the environment) */
+SPL_API int spl_debug_umma_acc(spl_handle* h, float* host_out, size_t n_floats);
+/* SYNCHRONOUS (tests only): 0 = no kernel of this handle ever timed out on an internal barrier */
+SPL_API int spl_debug_status(spl_handle* h);
 SPL_API int spl_feature_dim(const spl_handle* h);       /* D_out */
 SPL_API int spl_abi_version(void);
 SPL_API const char* spl_last_error(void);

@@ -1,0 +1,917 @@
+// Kernel A, default engine: the spectral stage as a folded real DFT on the 5th-generation tensor cores
+// (tcgen05.mma kind::f16, accumulators in TMEM), warp specialised, persistent, multi-batch.
+//
+// Path: src/third_party/kaldi_signal.py:163-211 (dither -> DC removal -> pre-emphasis -> window -> pad) and
+// :510-552 (rfft -> power -> mel -> log) + the pad/stack loop of src/blocks/sp_layers.py:81-91, for up to
+// kMaxBatches padded batches per launch.
+//
+// Arithmetic (validated on the CPU by tools/emulate_umma.py against the oracle, max |d| 5e-4 on log-mel):
+//   * a frame's origin is moved to the 16-byte floor of its first sample (shift h = 0..3 floats / 0..7 int16): the
+//     window table of shift h is the window delayed by h, the power spectrum does not change, and every
+//     shared-memory load of the samples is an aligned 128-bit load;
+//   * x~ = s (x - mu_c) + s d g : pivot mu_c (mean of the warp's sample span) and power-of-two scale s per
+//     producer warp (8 frames), noise g (kaldi_signal.py:176-177) from Philox4x32-7, eight 16-bit uniforms per call;
+//   * z'_j = w_j (x~_j - c x~_{j-1})   (x~_{-1} := x~_0), WITHOUT the mean: with N = padded size, NB = N/2, HALF = N/4
+//       a_j = z'_j + z'_{N-j},  b_j = z'_j - z'_{N-j}   (j = 0 .. NB-1)
+//       Ce_k = sum_{j even} a_j cos(2 pi jk/N)   Co_k = sum_{j odd} a_j cos(..)     k = 1 .. HALF
+//       Se_k = sum_{j even} b_j sin(2 pi jk/N)   So_k = sum_{j odd} b_j sin(..)
+//       X_k = (Ce + Co) - i (Se + So),   X_{NB-k} = (Ce - Co) - i (So - Se)
+//     four [128 frames x HALF] accumulators = all 512 TMEM columns at 16 kHz;
+//   * both operands are split into FP16 hi + lo (3 products, fp32 accumulation): 22 mantissa bits, K = 16 per MMA;
+//   * the DC removal x - mean(x) (mean of the NOISY frame) and the Nyquist-position sample z'_{NB} are folded
+//     into the GEMM as one extra K step: the A row holds -(1-c) mean(x~) (hi, lo) in the slots of its shift and
+//     z'_{NB} (hi, lo); the B image holds the DFT of the delayed window and (-1)^k.  No pre-pass over the frame is
+//     needed: the mean is accumulated while the operand is produced;
+//   * epilogue, thread per frame: TMEM -> power of bins 1..NB-1 in ascending order (two passes over the
+//     accumulators) -> streaming triangular mel bank (two running filters, weights from the reference's dense
+//     bank) -> log -> 16-column pieces through shared memory -> coalesced stores + fp64 column sums.
+//
+// Roles (one CTA of 23 warps per SM): warps 0-15 produce the A operand (warp w owns rows 8w..8w+7 of the
+// 128-row tile, lane = (row, octet of 8 samples)); warp 16 issues the MMAs; warp 17 streams the pre-swizzled
+// twiddle images (TMA bulk copies, 3-deep ring); warp 18 builds the tile (row table, sample staging by TMA);
+// warps 19-22 run the epilogue of tile i while the producers work on tile i+1.
+#include <cuda_fp16.h>
+
+#include "fbank_frame.cuh"
+#include "tc_common.cuh"
+
+namespace spl {
+
+namespace {
+
+constexpr int kURows = 128;
+constexpr int kUProd = 16;                  // producer warps
+constexpr int kUWarps = kUProd + 3 + 4;     // + MMA, twiddle TMA, tile setup, 4 epilogue warps
+constexpr int kUThreads = kUWarps * 32;
+constexpr int kBStages = 3;                 // twiddle half-stages in flight
+constexpr int kMaxSeg = 16;                 // utterance segments per tile (more: the tile is cut short)
+constexpr unsigned long long kWaitCycles = 1ull << 31;  // ~1 s: a wait that long is a protocol bug, not a stall
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory layout (byte offsets from the 1024-byte aligned base)
+struct ULayout {
+  int a_sub;       // one A sub-tile: 128 rows x 32 B
+  int a_stage;     // 8 sub-tiles: ce_hi ce_lo co_hi co_lo se_hi se_lo so_hi so_lo
+  int b_tile;      // one twiddle tile: HALF rows x 32 B
+  int b_stage;     // half-stage: 4 tiles
+  int off_a, off_b, off_samp, samp_bytes, off_tab, off_stg, off_rt, off_seg, off_fpre, off_gst, off_bar, total;
+};
+
+// row table of one tile (double buffered)
+struct RowTab {
+  float* out[kURows];    // destination of the row's features (nullptr: row not valid)
+  int off[kURows];       // element index (sample units) of the row's 16-byte floor inside the staging buffer
+  int ut[kURows];        // flattened utterance | shift h << 24 ; -1: invalid row
+  int t[kURows];         // frame index inside the utterance
+  float inv2[kURows];    // 1 / s^2 of the row (written by its producer warp)
+  int nrows;             // 0: no more tiles
+  int pad_[3];
+};
+
+__host__ __device__ inline ULayout make_ulayout(int nfft, int es, int tab_bytes, int D_out) {
+  ULayout L;
+  const int half = nfft / 4;
+  L.a_sub = kURows * 32;
+  L.a_stage = 8 * L.a_sub;
+  L.b_tile = half * 32;
+  L.b_stage = 4 * L.b_tile;
+  L.off_a = 0;
+  L.off_b = L.off_a + 2 * L.a_stage;
+  L.off_samp = L.off_b + kBStages * L.b_stage;
+  // staging: a full tile of one utterance ((127 S + Nw) samples at 16 kHz / fp32 = 82 880 B) + alignment heads
+  L.samp_bytes = es == 4 ? 86016 : 45056;
+  L.off_tab = L.off_samp + L.samp_bytes;
+  L.off_stg = (L.off_tab + tab_bytes + 15) & ~15;
+  L.off_rt = (L.off_stg + 4 * 32 * 17 * 4 + 15) & ~15;
+  L.off_seg = L.off_rt + 2 * (int)sizeof(RowTab);
+  L.off_fpre = L.off_seg + kMaxSeg * 16;
+  L.off_gst = (L.off_fpre + (kMaxUmmaUtts + 1) * 4 + 7) & ~7;
+  L.off_bar = L.off_gst + 2 * D_out * 8;
+  L.total = L.off_bar + 32 * 8;
+  return L;
+}
+
+// barrier indices
+enum : int {
+  BAR_TAB = 0,       // tables landed (TMA tx)
+  BAR_AFULL = 1,     // [2] producers -> MMA (16 arrivals)
+  BAR_AEMPTY = 3,    // [2] MMA commit -> producers
+  BAR_BFULL = 5,     // [3] twiddle TMA tx -> MMA
+  BAR_BEMPTY = 8,    // [3] MMA commit -> twiddle TMA
+  BAR_TFULL = 11,    // accumulators complete (commit) -> epilogue
+  BAR_TEMPTY = 12,   // epilogue drained TMEM (4 arrivals) -> MMA
+  BAR_SFULL = 13,    // samples landed (TMA tx) -> producers
+  BAR_SEMPTY = 14,   // producers done with the staging buffer (16 arrivals) -> setup warp
+  BAR_READY = 15,    // [2] tile published (1 arrival) -> everyone
+  BAR_COUNT = 17
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Bounded wait: a protocol error must not hang the GPU.  Returns false on timeout or when another role aborted.
+__device__ __forceinline__ bool mbar_wait_or_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code = 0) {
+  const uint32_t addr = smem_u32(bar);
+  unsigned long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if ((it & 63u) == 63u) {
+      if (*abort_flag) return false;
+      const unsigned long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitCycles) {
+        if (*abort_flag == 0) *abort_flag = 0x10000 | code;  // which wait gave up first: barrier index | warp << 8
+        return false;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16, FP16 operands, fp32 accumulate, A and B K-major, M = 128, N = n
+__device__ __host__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {  // (lo -> bits 0..15, hi -> bits 16..31)
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// v[0..3] -> FP16 hi parts (2 words) and FP16 lo parts (2 words) of the hi/lo split
+__device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
+  const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+// eight consecutive staged samples (aligned) as floats
+template <typename ST>
+__device__ __forceinline__ void load8(const ST* p, float (&x)[8]) {
+  if constexpr (sizeof(ST) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[2 * i] = (float)(short)(w[i] & 0xffffu);
+      x[2 * i + 1] = (float)((int)w[i] >> 16);
+    }
+  }
+}
+
+// batch of flattened utterance u (uniform loop over <= kMaxBatches descriptors)
+__device__ __forceinline__ int batch_of(const UmmaParams& p, int u) {
+  int k = 0;
+#pragma unroll 1
+  for (int i = 1; i < p.nb; ++i)
+    if (u >= p.bd[i].u0) k = i;
+  return k;
+}
+
+}  // namespace
+
+size_t fbank_umma_smem_bytes(int nfft, int es, int tab_bytes, int D_out) {
+  return (size_t)make_ulayout(nfft, es, tab_bytes, D_out).total + 1024;  // + alignment slack
+}
+
+// ---------------------------------------------------------------------------------------------
+// NOISE: 0 none, 1 device RNG (Philox), 2 host stream (parity mode: noise[b][t][Nw] of every batch)
+template <int NFFT, typename ST, int NOISE>
+__global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_constant__ UmmaParams p) {
+  constexpr int HALF = NFFT / 4, NB = NFFT / 2, NCH = NB / 32;
+  constexpr int TMEM_COLS = 4 * HALF;
+  constexpr int ES = (int)sizeof(ST);
+  constexpr int NSHIFT = 16 / ES;            // 4 (fp32) or 8 (int16)
+  constexpr int KX = (3 * NSHIFT + 2 + 15) / 16;  // K steps of the correction chunk
+  constexpr int HS_PER_TILE = 2 * (NCH + 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const ULayout L = make_ulayout(NFFT, ES, p.tab_bytes, p.D_out);
+  ST* samp = reinterpret_cast<ST*>(sm + L.off_samp);
+  const float* tab = reinterpret_cast<const float*>(sm + L.off_tab);
+  const float* wtab = tab;                                              // [NSHIFT][NFFT] delayed windows
+  const float2* melw = reinterpret_cast<const float2*>(tab + p.off_melw);   // [2 HALF] (w_a, w_b) per step
+  const uint32_t* melc = reinterpret_cast<const uint32_t*>(tab + p.off_melc);  // 2 bits per step: shifts before it
+  RowTab* rtab = reinterpret_cast<RowTab*>(sm + L.off_rt);
+  int4* segs = reinterpret_cast<int4*>(sm + L.off_seg);
+  int* fpre = reinterpret_cast<int*>(sm + L.off_fpre);
+  double* gst = reinterpret_cast<double*>(sm + L.off_gst);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.off_bar);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tslot + 1);
+  int* gcount = reinterpret_cast<int*>(tslot + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int S = p.S, Nw = p.Nw, D_out = p.D_out, U = p.total_utts;
+
+  // ---- 0. barriers, TMEM, tables, frame prefix ------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(bars + BAR_TAB, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + BAR_AFULL + i, kUProd);
+      mbar_init(bars + BAR_AEMPTY + i, 1);
+      mbar_init(bars + BAR_READY + i, 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(bars + BAR_BFULL + i, 1);
+      mbar_init(bars + BAR_BEMPTY + i, 1);
+    }
+    mbar_init(bars + BAR_TFULL, 1);
+    mbar_init(bars + BAR_TEMPTY, 4);
+    mbar_init(bars + BAR_SFULL, 1);
+    mbar_init(bars + BAR_SEMPTY, kUProd);
+    *abort_flag = 0;
+    *gcount = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bars + BAR_TAB, (uint32_t)p.tab_bytes);
+    bulk_g2s(sm + L.off_tab, p.tab, (uint32_t)p.tab_bytes, bars + BAR_TAB);
+  }
+  if (w == kUProd) tc::tmem_alloc<TMEM_COLS>(tslot);
+  if (w == 0) {  // frames of every flattened utterance, exclusive prefix; all loads issued before the scan
+    int carry = 0;
+    for (int base = 0; base < U; base += 32) {
+      const int u = base + lane;
+      int m = 0;
+      if (u < U) {
+        const int k = batch_of(p, u);
+        const UBatch& bd = p.bd[k];
+        const long long n = bd.wav_len[u - bd.u0];
+        m = n >= Nw ? (int)(1 + (n - Nw) / S) : 0;  // kaldi_signal.py:90
+        m = m > bd.T ? bd.T : m;
+        if (blockIdx.x == 0 && bd.feat_len) bd.feat_len[u - bd.u0] = m;
+      }
+      int inc = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (u < U) fpre[u] = carry + inc - m;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) fpre[U] = carry;
+  }
+  for (int i = tid; i < 2 * D_out; i += kUThreads) gst[i] = 0.0;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tslot;
+  const long long total = fpre[U];
+  const int r0 = (int)(total * blockIdx.x / gridDim.x), r1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+
+  // =================================================================================================
+  if (w < kUProd) {
+    // ---- producers ------------------------------------------------------------------------------
+    // zero padding rows (sp_layers.py:88): this CTA's equal share, one sixteenth per warp, written while the
+    // first tile's samples are in flight
+    {
+      long long tot_rows = 0;
+      for (int k = 0; k < p.nb; ++k) tot_rows += (long long)p.bd[k].B * p.bd[k].T;
+      const long long total_pad = tot_rows - total;
+      const long long c0 = total_pad * blockIdx.x / gridDim.x, c1 = total_pad * (blockIdx.x + 1) / gridDim.x;
+      long long q = c0 + (c1 - c0) * w / kUProd;
+      const long long q1 = c0 + (c1 - c0) * (w + 1) / kUProd;
+      if (q < q1) {
+        auto rows_before = [&](int u) -> long long {  // output rows of all utterances < u
+          long long rb = 0;
+          for (int k = 0; k < p.nb; ++k) {
+            const int cnt = u - p.bd[k].u0;
+            if (cnt > 0) rb += (long long)(cnt < p.bd[k].B ? cnt : p.bd[k].B) * p.bd[k].T;
+          }
+          return rb;
+        };
+        int lo = 0, hi = U - 1;  // largest u with pad rows before it <= q
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (rows_before(mid) - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        int u = lo;
+        while (q < q1) {
+          while (u + 1 < U && rows_before(u + 1) - fpre[u + 1] <= q) ++u;
+          const int k = batch_of(p, u);
+          const UBatch& bd = p.bd[k];
+          const int m_u = fpre[u + 1] - fpre[u];
+          const long long ofs = q - (rows_before(u) - fpre[u]);
+          long long nrows = (bd.T - m_u) - ofs;
+          nrows = nrows > q1 - q ? q1 - q : nrows;
+          float* dst = bd.feats + ((size_t)(u - bd.u0) * bd.T + m_u + (size_t)ofs) * D_out;
+          const long long nfl = nrows * D_out;
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nfl & 3) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (long long i = lane; i < (nfl >> 2); i += 32) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            for (long long i = lane; i < nfl; i += 32) dst[i] = 0.f;
+          }
+          q += nrows;
+        }
+      }
+    }
+    if (!mbar_wait_or_abort(bars + BAR_TAB, 0, abort_flag, BAR_TAB | (w << 8))) goto done;
+    {
+      const int rl = lane >> 2, q = lane & 3;   // row inside the warp, octet inside the chunk
+      const int row = 8 * w + rl;
+      const float cpre = p.preemph;
+      const float dith = p.dither;
+      uint32_t chunk_seq = 0;                   // A stages used so far
+      for (int tile = 0;; ++tile) {
+        const int slot = tile & 1;
+        if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) goto done;
+        RowTab& rt = rtab[slot];
+        const int nrows = rt.nrows;
+        if (nrows == 0) break;
+        if (!mbar_wait_or_abort(bars + BAR_SFULL, tile & 1, abort_flag, BAR_SFULL | (w << 8))) goto done;  // the tile's samples have landed
+        const bool rvalid = row < nrows;
+        // rows past the tile's end mirror the warp's first row (finite data, results never stored)
+        const int rsrc = rvalid ? row : (8 * w < nrows ? 8 * w : 0);
+        const int roff = rt.off[rsrc];
+        const int ut = rt.ut[rsrc];
+        const int h = ut >> 24, uflat = ut & 0xffffff;
+        const int tfr = rt.t[rsrc];
+        const ST* xrow = samp + roff;
+        const float* wrow = wtab + h * NFFT;
+        const int hNw = h + Nw;
+
+        // pass 1: max |x| and mean over the warp's sample span -> power-of-two scale, pivot
+        float sc, piv;
+        {
+          const int lo_off = __shfl_sync(0xffffffffu, roff, 0);
+          const int wrows = nrows - 8 * w >= 8 ? 8 : (nrows - 8 * w > 0 ? nrows - 8 * w : 1);
+          const int hi_off = __shfl_sync(0xffffffffu, roff + hNw, 4 * (wrows - 1));
+          const int first = lo_off + __shfl_sync(0xffffffffu, h, 0);  // first real sample of the span
+          const int n8 = (hi_off - lo_off + 7) >> 3;  // octets; elements outside [first, hi_off) may be foreign memory
+          float mx = 0.f, sm_ = 0.f;
+          for (int i = lane; i < n8; i += 32) {
+            float v[8];
+            load8<ST>(samp + lo_off + 8 * i, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int idx = lo_off + 8 * i + e;
+              const float ve = (idx >= first && idx < hi_off) ? v[e] : 0.f;
+              mx = fmaxf(mx, fabsf(ve));
+              sm_ += ve;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
+          }
+          piv = sm_ / (float)(hi_off - first);
+          if (!(fabsf(piv) <= 3.0e38f) || !p.remove_dc) piv = 0.f;  // NaN / Inf samples: no pivot
+          // |a| <= 4 max|x~|, |x~| <= 2 max|x| + 6 |dither|  ->  scaled operand below 2^13
+          const float bound = 4.f * (2.f * mx + 6.f * fabsf(dith));
+          int e = 13 - (bound > 0.f && bound < 3.0e38f ? (int)ceilf(log2f(bound)) : 0);
+          e = e > 60 ? 60 : (e < -60 ? -60 : e);
+          sc = __int_as_float((127 + e) << 23);
+          if (q == 0 && rvalid) rt.inv2[row] = __int_as_float((127 - 2 * e) << 23);
+        }
+        const float so = -piv * sc;
+        float rowsum = 0.f, zhalf = 0.f;
+        float carry_j = 0.f, carry_m = 0.f;   // previous chunk's last x~ (lane q = 3) / lowest mirrored x~
+        [[maybe_unused]] const float nk = 1.3862943611198906f * sc * sc * dith * dith;   // 2 ln 2 (s d)^2
+        [[maybe_unused]] const float nsgn = dith < 0.f ? -1.f : 1.f;
+        [[maybe_unused]] const float* nzrow = nullptr;
+        if constexpr (NOISE == 2) {
+          const UBatch& bd = p.bd[batch_of(p, uflat)];
+          nzrow = bd.noise + ((size_t)(uflat - bd.u0) * bd.T + tfr) * Nw - h;  // indexed by shifted position
+        }
+        // noise for the eight positions pos0 .. pos0+7 (valid: h <= pos < h + Nw), added to x
+        auto add_noise = [&](float (&x)[8], int pos0, uint32_t block_id) {
+          if constexpr (NOISE == 1) {
+            const uint4 r = philox4x32_7(make_uint4(block_id, (uint32_t)tfr, (uint32_t)uflat, 0x5eedu), p.seed_lo, p.seed_hi);
+            const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float vf = (float)((i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xffffu)) + 0.5f;  // u = vf 2^-16
+              const float a = fmaf(fast_log2(vf), -nk, 16.0001f * nk);  // -2 ln u (s d)^2 > 0
+              float cs;
+              asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(vf * 9.587379924285257e-05f));  // 2 pi 2^-16
+              x[i] = fmaf(fast_sqrt(a) * cs, nsgn, x[i]);
+            }
+          } else if constexpr (NOISE == 2) {
+            const float sd = sc * dith;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int pos = pos0 + i;
+              if (pos >= h && pos < hNw) x[i] = fmaf(__ldg(nzrow + pos), sd, x[i]);
+            }
+          }
+          (void)pos0;
+          (void)block_id;
+        };
+
+#pragma unroll 1
+        for (int c = 0; c <= NCH; ++c, ++chunk_seq) {
+          const int st = chunk_seq & 1;
+          uint8_t* stage = sm + L.off_a + st * L.a_stage;
+          if (chunk_seq >= 2 && !mbar_wait_or_abort(bars + BAR_AEMPTY + st, ((chunk_seq >> 1) - 1) & 1, abort_flag, BAR_AEMPTY | (w << 8))) goto done;
+          // byte offset of this lane's 8-byte slice (K columns 4q..4q+3) inside a sub-tile (SWIZZLE_32B)
+          const uint32_t aoff = (uint32_t)(row * 32 + ((((q >> 1) ^ (row >> 2)) & 1) << 4) + ((q & 1) << 3));
+          if (c < NCH) {
+            const int j0 = 32 * c + 8 * q;
+            // ---- direct part: positions j0 .. j0+7 ----
+            float x[8];
+            load8<ST>(xrow + j0, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sc, so);
+            add_noise(x, j0, (uint32_t)(4 * c + q));
+            if (c == 0) {  // positions before the frame's first sample: excluded from the mean, replicate x~_h
+              float xh = x[0];
+#pragma unroll
+              for (int i = 1; i < NSHIFT; ++i) xh = (i == h) ? x[i] : xh;
+#pragma unroll
+              for (int i = 0; i < NSHIFT - 1; ++i)
+                if (q == 0 && i < h) {  // replaced by x~_h and taken out of the sum that follows
+                  x[i] = xh;
+                  rowsum -= xh;
+                }
+            }
+            rowsum += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+            float pv = __shfl_up_sync(0xffffffffu, x[7], 1, 4);
+            if (q == 0) pv = (c == 0) ? x[0] : carry_j;
+            carry_j = __shfl_sync(0xffffffffu, x[7], 3, 4);
+            float zj[8];
+            {
+              const float4 w0 = *reinterpret_cast<const float4*>(wrow + j0), w1 = *reinterpret_cast<const float4*>(wrow + j0 + 4);
+              const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) zj[i] = wv[i] * fmaf(-cpre, i == 0 ? pv : x[i - 1], x[i]);
+            }
+            // ---- mirrored part: positions N-8-j0 .. N-1-j0 (+ the one above, from the neighbour octet) ----
+            const bool mirror = NFFT - 32 * c - 32 < Nw + NSHIFT - 1;  // uniform: some octet of the chunk is live
+            float zm[8];  // zm[i] pairs with zj[i]: position N - (j0 + i)
+            if (mirror) {
+              const int p0 = NFFT - 8 - j0;
+              float y[8];
+              load8<ST>(xrow + p0, y);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], sc, so);
+              add_noise(y, p0, (uint32_t)(NFFT / 8 + 4 * c + q));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = (p0 + i < hNw) ? y[i] : 0.f;
+              rowsum += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
+              float top = __shfl_up_sync(0xffffffffu, y[0], 1, 4);  // position N - j0: lowest of the octet above
+              if (q == 0) top = carry_m;
+              carry_m = __shfl_sync(0xffffffffu, y[0], 3, 4);
+              const float4 w0 = *reinterpret_cast<const float4*>(wrow + p0), w1 = *reinterpret_cast<const float4*>(wrow + p0 + 4);
+              const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              // position p0 + e (e = 1..8; e = 8 is `top`) pairs with the direct position j0 + 8 - e
+              const float wtop = (j0 > 0) ? wrow[NFFT - j0] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 7; ++i) zm[7 - i] = wv[i + 1] * fmaf(-cpre, y[i], y[i + 1]);  // position p0 + 1 + i
+              zm[0] = (j0 > 0) ? wtop * fmaf(-cpre, y[7], top) : 0.f;                          // position N - j0
+              if (c == NCH - 1 && q == 3) zhalf = wv[0] * fmaf(-cpre, x[7], y[0]);  // position NB: prev is x~_{NB-1}
+            } else {
+              carry_m = 0.f;
+            }
+            // ---- fold, split, store ----
+            float ae[4], ao[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ae[i] = mirror ? zj[2 * i] + zm[2 * i] : zj[2 * i];
+              ao[i] = mirror ? zj[2 * i + 1] + zm[2 * i + 1] : zj[2 * i + 1];
+            }
+            uint2 hi, lo;
+            split4(ae, hi, lo);
+            *reinterpret_cast<uint2*>(stage + 0 * L.a_sub + aoff) = hi;
+            *reinterpret_cast<uint2*>(stage + 1 * L.a_sub + aoff) = lo;
+            split4(ao, hi, lo);
+            *reinterpret_cast<uint2*>(stage + 2 * L.a_sub + aoff) = hi;
+            *reinterpret_cast<uint2*>(stage + 3 * L.a_sub + aoff) = lo;
+            if (mirror) {
+              float be[4], bo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                be[i] = zj[2 * i] - zm[2 * i];
+                bo[i] = zj[2 * i + 1] - zm[2 * i + 1];
+              }
+              split4(be, hi, lo);
+              *reinterpret_cast<uint2*>(stage + 4 * L.a_sub + aoff) = hi;
+              *reinterpret_cast<uint2*>(stage + 5 * L.a_sub + aoff) = lo;
+              split4(bo, hi, lo);
+              *reinterpret_cast<uint2*>(stage + 6 * L.a_sub + aoff) = hi;
+              *reinterpret_cast<uint2*>(stage + 7 * L.a_sub + aoff) = lo;
+            }
+          } else {
+            // ---- correction chunk: -(1-c) mean(x~) in the slots of shift h, z'_{NB} in the last two ----
+            float rs = rowsum;
+            rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+            const float g = p.remove_dc ? -(1.f - cpre) * rs / (float)Nw : 0.f;
+            const float zh = __shfl_sync(0xffffffffu, zhalf, 3, 4);
+            const __half gh = __float2half_rn(g), zhh = __float2half_rn(zh);
+            const __half gl = __float2half_rn(g - __half2float(gh)), zhl = __float2half_rn(zh - __half2float(zhh));
+#pragma unroll
+            for (int kx = 0; kx < KX; ++kx) {
+              __half v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int s_ = 16 * kx + 4 * q + i;  // slot
+                __half val = __float2half_rn(0.f);
+                if (s_ < 3 * NSHIFT) {
+                  if (s_ / 3 == h) val = (s_ % 3 == 1) ? gl : gh;
+                } else if (s_ == 3 * NSHIFT) val = zhh;
+                else if (s_ == 3 * NSHIFT + 1) val = zhl;
+                v[i] = val;
+              }
+              uint2 wv;
+              wv.x = (uint32_t)__half_as_ushort(v[0]) | ((uint32_t)__half_as_ushort(v[1]) << 16);
+              wv.y = (uint32_t)__half_as_ushort(v[2]) | ((uint32_t)__half_as_ushort(v[3]) << 16);
+              *reinterpret_cast<uint2*>(stage + kx * L.a_sub + aoff) = wv;
+            }
+          }
+          fence_proxy_async();  // generic-proxy writes of the A tiles -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bars + BAR_AFULL + st);
+            if (c == NCH - 1) mbar_arrive(bars + BAR_SEMPTY);  // every lane's last read of the staging buffer is done
+          }
+        }
+      }
+    }
+  } else if (w == kUProd) {
+    // ---- MMA issuer ---------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(HALF);
+      const uint32_t a_base = tc::smem_addr(sm + L.off_a), b_base = tc::smem_addr(sm + L.off_b);
+      uint32_t chunk_seq = 0, hs_seq = 0;
+      for (int tile = 0;; ++tile) {
+        const int slot = tile & 1;
+        if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) break;
+        if (rtab[slot].nrows == 0) break;
+        if (tile > 0 && !mbar_wait_or_abort(bars + BAR_TEMPTY, (tile - 1) & 1, abort_flag, BAR_TEMPTY | (w << 8))) break;
+        tc::fence_after_sync();
+        bool ok = true;
+        for (int c = 0; c <= NCH && ok; ++c, ++chunk_seq) {
+          const int st = chunk_seq & 1;
+          if (!mbar_wait_or_abort(bars + BAR_AFULL + st, (chunk_seq >> 1) & 1, abort_flag, BAR_AFULL | (w << 8))) { ok = false; break; }
+          const uint32_t a_st = a_base + st * L.a_stage;
+          const bool mirror = c < NCH && (NFFT - 32 * c - 32 < Nw + NSHIFT - 1);
+          for (int hf = 0; hf < 2; ++hf, ++hs_seq) {
+            const int bs = hs_seq % kBStages;
+            if (!mbar_wait_or_abort(bars + BAR_BFULL + bs, (hs_seq / kBStages) & 1, abort_flag, BAR_BFULL | (w << 8))) { ok = false; break; }
+            tc::fence_after_sync();
+            const uint32_t b_st = b_base + bs * L.b_stage;
+            if (c < NCH) {
+#pragma unroll
+              for (int pp = 0; pp < 2; ++pp) {  // even / odd block of this half (cos: 0, 1; sin: 2, 3)
+                const int blk = 2 * hf + pp;
+                const int asub = (hf == 1 && !mirror) ? 2 * pp : 2 * blk;  // no mirror: b == a, reuse the cos operand
+                const uint64_t ahi = tc::make_desc_sw32(a_st + asub * L.a_sub), alo = tc::make_desc_sw32(a_st + (asub + 1) * L.a_sub);
+                const uint64_t bhi = tc::make_desc_sw32(b_st + (2 * pp) * L.b_tile), blo = tc::make_desc_sw32(b_st + (2 * pp + 1) * L.b_tile);
+                const uint32_t d = tmem + blk * HALF;
+                mma_f16(d, ahi, bhi, idesc, c > 0);
+                mma_f16(d, alo, bhi, idesc, 1);
+                mma_f16(d, ahi, blo, idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                for (int kx = 0; kx < KX; ++kx)
+                  mma_f16(tmem + (2 * hf + pp) * HALF, tc::make_desc_sw32(a_st + kx * L.a_sub),
+                          tc::make_desc_sw32(b_st + (kx * 2 + pp) * L.b_tile), idesc, 1);
+            }
+            tc::commit(bars + BAR_BEMPTY + bs);
+          }
+          if (!ok) break;
+          tc::commit(bars + BAR_AEMPTY + st);
+        }
+        if (!ok) break;
+        tc::commit(bars + BAR_TFULL);
+      }
+    }
+    __syncwarp();
+  } else if (w == kUProd + 1) {
+    // ---- twiddle stream: half-stage i of a tile = image i, the same for every tile ------------------
+    if (lane == 0) {
+      uint32_t hs_seq = 0;
+      for (int tile = 0;; ++tile) {
+        const int slot = tile & 1;
+        if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) break;
+        if (rtab[slot].nrows == 0) break;
+        bool ok = true;
+        for (int i = 0; i < HS_PER_TILE; ++i, ++hs_seq) {
+          const int bs = hs_seq % kBStages;
+          if (hs_seq >= kBStages && !mbar_wait_or_abort(bars + BAR_BEMPTY + bs, (hs_seq / kBStages - 1) & 1, abort_flag, BAR_BEMPTY | (w << 8))) { ok = false; break; }
+          mbar_expect_tx(bars + BAR_BFULL + bs, (uint32_t)L.b_stage);
+          bulk_g2s(sm + L.off_b + bs * L.b_stage, p.twiddles + (size_t)i * L.b_stage, (uint32_t)L.b_stage, bars + BAR_BFULL + bs);
+        }
+        if (!ok) break;
+      }
+    }
+    __syncwarp();
+  } else if (w == kUProd + 2) {
+    // ---- tile setup: row table, sample staging ---------------------------------------------------------
+    int pos = r0;
+    int u_hint = 0;
+    {
+      int lo = 0, hi = U - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (fpre[mid] <= pos) lo = mid; else hi = mid - 1;
+      }
+      u_hint = lo;
+    }
+    const int cap = L.samp_bytes / ES - 16;  // elements; the pass over a warp's span reads up to 7 past its end
+    for (int tile = 0;; ++tile) {
+      const int slot = tile & 1;
+      RowTab& rt = rtab[slot];
+      int nrows = 0, nseg = 0;
+      if (pos < r1) {
+        // lane 0 walks the utterance segments of the tile
+        if (lane == 0) {
+          int u = u_hint, used = 0, left = r1 - pos < kURows ? r1 - pos : kURows;
+          int g = pos;
+          while (left > 0 && nseg < kMaxSeg) {
+            while (fpre[u + 1] <= g) ++u;
+            const int k = batch_of(p, u);
+            const UBatch& bd = p.bd[k];
+            const int t0 = g - fpre[u];
+            int n = fpre[u + 1] - g;
+            n = n < left ? n : left;
+            const char* src = static_cast<const char*>(bd.wav) + ((size_t)(u - bd.u0) * bd.wav_pitch + (size_t)t0 * S) * ES;
+            const int head = (int)((reinterpret_cast<uintptr_t>(src) & 15) / ES);
+            // rows that fit in what is left of the staging buffer
+            const int room = cap - used - head - Nw;
+            if (room < 0) break;
+            const int fit = room / S + 1;
+            if (n > fit) n = fit;
+            const int span = head + (n - 1) * S + Nw;
+            const int span16 = ((span * ES + 15) & ~15) / ES;
+            segs[nseg] = make_int4(u, t0, n, used);
+            used += span16;
+            nrows += n;
+            left -= n;
+            g += n;
+            ++nseg;
+            if (n == fit && left > 0 && fpre[u + 1] > g) break;  // the buffer is full inside this utterance
+          }
+          u_hint = u;
+        }
+        nrows = __shfl_sync(0xffffffffu, nrows, 0);
+        nseg = __shfl_sync(0xffffffffu, nseg, 0);
+        u_hint = __shfl_sync(0xffffffffu, u_hint, 0);
+      }
+      if (tile > 0 && !mbar_wait_or_abort(bars + BAR_SEMPTY, (tile - 1) & 1, abort_flag, BAR_SEMPTY | (w << 8))) break;
+      __syncwarp();
+      if (nrows > 0) {
+        // stage the segments: TMA bulk copy from the 16-byte floor, or warp loads when the envelope would leave the batch
+        uint32_t tx = 0;
+        for (int s_ = 0; s_ < nseg; ++s_) {
+          const int4 sg = segs[s_];
+          const UBatch& bd = p.bd[batch_of(p, sg.x)];
+          const char* wav_lo = static_cast<const char*>(bd.wav);
+          const char* wav_hi = wav_lo + ((size_t)(bd.B - 1) * bd.wav_pitch + (size_t)bd.wav_cols) * ES;
+          const char* src = wav_lo + ((size_t)(sg.x - bd.u0) * bd.wav_pitch + (size_t)sg.y * S) * ES;
+          const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
+          const int head = (int)((src - a0) / ES);
+          const uint32_t bytes = (uint32_t)(((head + (sg.z - 1) * S + Nw) * ES + 15) & ~15);
+          ST* dst = samp + sg.w;
+          if (a0 >= wav_lo && a0 + bytes <= wav_hi) {
+            if (lane == 0) {
+              fence_proxy_async();
+              bulk_g2s(dst, a0, bytes, bars + BAR_SFULL);
+            }
+            tx += bytes;
+          } else {
+            const ST* s0 = reinterpret_cast<const ST*>(src);
+            const int need = (sg.z - 1) * S + Nw;
+            for (int i = lane; i < head; i += 32) dst[i] = (ST)0;
+            for (int i = lane; i < need; i += 32) dst[head + i] = __ldg(s0 + i);
+            for (int i = head + need + lane; i < (int)(bytes / ES); i += 32) dst[i] = (ST)0;
+          }
+        }
+        if (lane == 0) mbar_expect_tx(bars + BAR_SFULL, tx);  // tx == 0: plain arrival
+        // row table while the copies are in flight
+        for (int r = lane; r < kURows; r += 32) {
+          int ut = -1, off = 0, tt = 0;
+          float* out = nullptr;
+          if (r < nrows) {
+            int acc = 0, s_ = 0;
+            while (acc + segs[s_].z <= r) acc += segs[s_++].z;
+            const int4 sg = segs[s_];
+            const UBatch& bd = p.bd[batch_of(p, sg.x)];
+            const char* src = static_cast<const char*>(bd.wav) + ((size_t)(sg.x - bd.u0) * bd.wav_pitch + (size_t)sg.y * S) * ES;
+            const int head = (int)((reinterpret_cast<uintptr_t>(src) & 15) / ES);
+            const int e0 = sg.w + head + (r - acc) * S;  // first sample of the row
+            off = e0 & ~(16 / ES - 1);
+            ut = sg.x | ((e0 - off) << 24);
+            tt = sg.y + (r - acc);
+            out = bd.feats + ((size_t)(sg.x - bd.u0) * bd.T + tt) * D_out;
+          }
+          rt.out[r] = out;
+          rt.off[r] = off;
+          rt.ut[r] = ut;
+          rt.t[r] = tt;
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        rt.nrows = nrows;
+        __threadfence_block();
+        mbar_arrive(bars + BAR_READY + slot);
+      }
+      __syncwarp();
+      if (nrows == 0) break;
+      pos += nrows;
+    }
+  } else {
+    // ---- epilogue: thread per frame --------------------------------------------------------------------
+    const int wq = w & 3;                       // TMEM lane quarter this warp may access
+    const int row = 32 * wq + lane;
+    float* stg = reinterpret_cast<float*>(sm + L.off_stg) + wq * 32 * 17;
+    const bool want_utt = p.want_utt_stats != 0, want_g = p.global_stats != nullptr;
+    int my_rows = 0;
+    for (int tile = 0;; ++tile) {
+      const int slot = tile & 1;
+      if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) goto done;
+      RowTab& rt = rtab[slot];
+      const int nrows = rt.nrows;
+      if (nrows == 0) break;
+      if (!mbar_wait_or_abort(bars + BAR_TFULL, tile & 1, abort_flag, BAR_TFULL | (w << 8))) goto done;
+      tc::fence_after_sync();
+      const float inv2 = row < nrows ? rt.inv2[row] : 1.f;
+      if (wq == 0 && lane == 0) my_rows += nrows;
+      float accA = 0.f, accB = 0.f;
+      int col = 0;
+      // store + column sums of the 16-column piece [c0, c0 + n) staged by this warp
+      auto flush_piece = [&](int c0, int n) {
+        __syncwarp();
+        const int c = lane & 15, hf = lane >> 4;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int r = 2 * it + hf;
+          float* o = rt.out[32 * wq + r];
+          if (c < n && o != nullptr) o[c0 + c] = stg[r * 17 + c];
+        }
+        if ((want_utt || want_g) && c < n) {
+          double s1 = 0.0, s2 = 0.0, g1 = 0.0, g2 = 0.0;
+          int cu = -1;
+          auto push = [&]() {
+            if (cu >= 0 && want_utt) {
+              const UBatch& bd = p.bd[batch_of(p, cu)];
+              if (bd.utt_stats) {
+                atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + c0 + c, s1);
+                atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + c0 + c, s2);
+              }
+            }
+            g1 += s1;
+            g2 += s2;
+            s1 = s2 = 0.0;
+          };
+          for (int i = 0; i < 16; ++i) {
+            const int r = 16 * hf + i;
+            const int ut = rt.ut[32 * wq + r];
+            const int u = ut < 0 ? -1 : (ut & 0xffffff);
+            if (u != cu) {
+              push();
+              cu = u;
+            }
+            if (u >= 0) {
+              const double v = (double)stg[r * 17 + c];
+              s1 += v;
+              s2 = fma(v, v, s2);
+            }
+          }
+          push();
+          if (want_g) {
+            atomicAdd(gst + c0 + c, g1);
+            atomicAdd(gst + D_out + c0 + c, g2);
+          }
+        }
+        __syncwarp();
+      };
+      auto emit = [&]() {
+        stg[lane * 17 + (col & 15)] = fast_log(fmaxf(accA * inv2, kEps));  // kaldi_signal.py:540
+        accA = accB;
+        accB = 0.f;
+        ++col;
+        if ((col & 15) == 0) flush_piece(col - 16, 16);
+      };
+      const uint32_t tbase = tmem + ((uint32_t)(32 * wq) << 16);
+      if (p.debug_acc != nullptr && blockIdx.x == 0 && tile == 0) {  // diagnostic: raw accumulators [row][4 HALF] + 1/s^2
+        for (int c8 = 0; c8 < 4 * HALF; c8 += 8) {
+          float v[8];
+          tmem_ld8(tbase + c8, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p.debug_acc[(size_t)row * (4 * HALF + 1) + c8 + i] = v[i];
+        }
+        p.debug_acc[(size_t)row * (4 * HALF + 1) + 4 * HALF] = inv2;
+      }
+#pragma unroll 1
+      for (int step0 = 0; step0 < 2 * HALF; step0 += 8) {
+        // pass 1 (step < HALF): bin = step + 1 = column + 1;  pass 2: bin = HALF + i, column = HALF - 1 - i
+        const bool second = step0 >= HALF;
+        const int c0 = second ? (2 * HALF - 8 - step0) : step0;  // first TMEM column of the 8 read here
+        float ce[8], co[8], se[8], so2[8];
+        tmem_ld8(tbase + c0, ce);
+        tmem_ld8(tbase + HALF + c0, co);
+        tmem_ld8(tbase + 2 * HALF + c0, se);
+        tmem_ld8(tbase + 3 * HALF + c0, so2);
+        tmem_ld_wait();
+        const uint32_t ctl = (melc[step0 >> 4] >> ((step0 & 8) << 1)) & 0xffffu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ci = second ? 7 - i : i;  // column inside the 8 (descending in pass 2)
+          const float re = second ? ce[ci] - co[ci] : ce[ci] + co[ci];
+          const float im = second ? so2[ci] - se[ci] : se[ci] + so2[ci];
+          const float pw = fmaf(re, re, im * im);
+          uint32_t ns = (ctl >> (2 * i)) & 3u;
+          while (ns) {  // uniform
+            emit();
+            --ns;
+          }
+          const float2 wv = melw[step0 + i];
+          accA = fmaf(wv.x, pw, accA);
+          accB = fmaf(wv.y, pw, accB);
+        }
+      }
+      // the accumulators of this tile are drained: the next tile's MMAs may overwrite them
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BAR_TEMPTY);
+      for (int i = 0; i < p.nflush; ++i) emit();
+      if (col & 15) flush_piece(col & ~15, col & 15);
+    }
+    if (want_g && wq == 0 && lane == 0) atomicAdd(gcount, my_rows);
+  }
+
+done:
+  tc::fence_before_sync();
+  __syncthreads();
+  if (p.global_stats != nullptr && !*abort_flag) {
+    for (int i = tid; i < 2 * D_out; i += kUThreads)
+      if (gst[i] != 0.0) atomicAdd(p.global_stats + i, gst[i]);
+    if (tid == 0 && *gcount) atomicAdd(p.global_stats + 2 * D_out, (double)*gcount);
+  }
+  if (*abort_flag && tid == 0 && p.status) atomicCAS(p.status, 0, *abort_flag);
+  if (w == kUProd) tc::tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NFFT, typename ST, int NOISE>
+static cudaError_t launch_uT(const UmmaParams& p, int num_ctas, cudaStream_t st) {
+  const size_t smem = fbank_umma_smem_bytes(NFFT, (int)sizeof(ST), p.tab_bytes, p.D_out);
+  static thread_local size_t configured[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || configured[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(fbank_umma_kernel<NFFT, ST, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev < 16) configured[dev] = smem;
+  }
+  fbank_umma_kernel<NFFT, ST, NOISE><<<num_ctas, kUThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int NFFT, typename ST>
+static cudaError_t launch_uN(const UmmaParams& p, int noise_mode, int num_ctas, cudaStream_t st) {
+  if (noise_mode == 0) return launch_uT<NFFT, ST, 0>(p, num_ctas, st);
+  if (noise_mode == 1) return launch_uT<NFFT, ST, 1>(p, num_ctas, st);
+  return launch_uT<NFFT, ST, 2>(p, num_ctas, st);
+}
+
+cudaError_t launch_fbank_umma(const UmmaParams& p, int nfft, int sample_format, int noise_mode, int num_ctas, cudaStream_t st) {
+  if (nfft == 512)
+    return sample_format == SPL_SAMPLES_F32 ? launch_uN<512, float>(p, noise_mode, num_ctas, st)
+                                            : launch_uN<512, int16_t>(p, noise_mode, num_ctas, st);
+  return sample_format == SPL_SAMPLES_F32 ? launch_uN<256, float>(p, noise_mode, num_ctas, st)
+                                          : launch_uN<256, int16_t>(p, noise_mode, num_ctas, st);
+}
+
+}  // namespace spl

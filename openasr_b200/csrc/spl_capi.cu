@@ -41,19 +41,29 @@ struct DeviceGuard {
 
 }  // namespace
 
+enum Engine { ENGINE_UMMA = 0, ENGINE_FFT = 1, ENGINE_SIMPLE = 2 };
+
 struct spl_handle {
   spl_config cfg;
   int device;
   int D_out;
   int num_sms;
-  int kernel;  // 0 warp-pipelined (default), 1 simple one-tile-per-CTA (SPL_LEGACY_KERNEL=1), 2 persistent CTA tiles (=2)
+  int engine;        // preferred kernel-A engine (SPL_ENGINE=umma|fft|simple; default umma)
+  bool fft_ok;       // the warp-pipelined FFT kernel fits this configuration
   size_t smem_warp;
   size_t smem_warp16;
-  size_t smem_pair;
   int ctas_per_sm;
-  void* blob;  // single device allocation holding every table
+  void* blob;        // single device allocation holding every table
+  int32_t* status;   // device word set by a kernel whose barrier wait timed out (spl_debug_status)
+  float* debug_acc;  // SPL_UMMA_DEBUG=1: raw accumulators of the first tile (spl_debug_umma_acc)
   spl::Tables tab;
   size_t smem_bytes;
+  // tcgen05 engine, per sample format (0 fp32, 1 int16): tables present, device pointers
+  bool umma_ok[2];
+  const uint8_t* umma_tw[2];
+  const float* umma_tab[2];
+  int umma_tab_bytes[2], umma_off_melw[2], umma_off_melc[2], umma_nflush;
+  int umma_ctas;     // grid of the tcgen05 engine (SM count; SPL_UMMA_CTAS overrides, diagnostics)
 };
 
 extern "C" {
@@ -108,53 +118,7 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     }
     grp[spl::kWarps] = D;
   }
-  // ---- persistent-kernel table block (see spl_internal.cuh) ----
   const int npairs = (D + 1) / 2;
-  std::vector<float> pw;          // pair weights
-  std::vector<uint32_t> pdesc(npairs);
-  std::vector<int> pcost(npairs);
-  for (int i = 0; i < npairs; ++i) {
-    int lo_[2], n4_[2];
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const int m = 2 * i + s2;
-      if (m < D && cnt[m] > 0) {
-        lo_[s2] = lo[m] & ~3;
-        n4_[s2] = (lo[m] + cnt[m] - lo_[s2] + 3) / 4;
-      } else {
-        lo_[s2] = 0;
-        n4_[s2] = 0;
-      }
-    }
-    const int n4p = n4_[0] > n4_[1] ? n4_[0] : n4_[1];
-    for (int s2 = 0; s2 < 2; ++s2)
-      if (lo_[s2] + 4 * n4p > nb) lo_[s2] = nb - 4 * n4p;  // keep the padded run inside the power row
-    const uint32_t off8 = (uint32_t)(pw.size() / 8);
-    for (int g = 0; g < n4p; ++g)
-      for (int s2 = 0; s2 < 2; ++s2)
-        for (int j = 0; j < 4; ++j) {
-          const int m = 2 * i + s2, k = lo_[s2] + 4 * g + j;
-          const bool in = m < D && k >= lo[m] && k < lo[m] + cnt[m];
-          pw.push_back(in ? 0.25f * mel_dense[(size_t)m * nb + k] : 0.f);
-        }
-    pdesc[i] = (uint32_t)(lo_[0] >> 2) | ((uint32_t)(lo_[1] >> 2) << 6) | ((uint32_t)n4p << 12) | (off8 << 18) |
-               ((2 * i + 1 < D) ? 0x80000000u : 0u);
-    pcost[i] = 14 + 15 * n4p;
-    if (n4p > 63 || off8 > 8191) return fail(SPL_ERR_UNSUPPORTED, "spl_create: mel bank too large for the descriptor");
-  }
-  int32_t pgrp[spl::kWarps + 1];
-  {
-    long total = 0;
-    for (int i = 0; i < npairs; ++i) total += pcost[i];
-    int i = 0;
-    long acc = 0;
-    pgrp[0] = 0;
-    for (int w = 1; w < spl::kWarps; ++w) {
-      const long target = total * w / spl::kWarps;
-      while (i < npairs && acc + pcost[i] / 2 < target) acc += pcost[i++];
-      pgrp[w] = i;
-    }
-    pgrp[spl::kWarps] = npairs;
-  }
   // ---- warp-pipelined kernel table block (see spl_internal.cuh) ----
   const int nj = (npairs + 7) / 8;
   std::vector<float> ww;
@@ -194,141 +158,6 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
       goff += n4j;
     }
   }
-  // ---- pair-pipelined kernel table block (see spl_internal.cuh / fbank_pair.cu) ----
-  std::vector<float> qw;
-  std::vector<uint32_t> qdesc;
-  int qE = 0;
-  if (nfft == 512) {
-    std::vector<int> lo4(D), n4(D), order(D);
-    for (int m = 0; m < D; ++m) {
-      lo4[m] = cnt[m] > 0 ? (lo[m] & ~3) : 0;
-      n4[m] = cnt[m] > 0 ? (lo[m] + cnt[m] - lo4[m] + 3) / 4 : 1;  // empty filters still emit log(eps)
-      if (lo4[m] + 4 * n4[m] > nb) lo4[m] = nb - 4 * n4[m];
-      order[m] = m;
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n4[a] > n4[b]; });
-    std::vector<std::vector<int>> streams(32);
-    std::vector<int> load(32, 0);
-    for (int m : order) {  // longest first onto the least-loaded stream
-      int best = 0;
-      for (int s2 = 1; s2 < 32; ++s2)
-        if (load[s2] < load[best]) best = s2;
-      streams[best].push_back(m);
-      load[best] += n4[m];
-    }
-    for (int s2 = 0; s2 < 32; ++s2) qE = load[s2] > qE ? load[s2] : qE;
-    qw.assign((size_t)qE * 32 * 4, 0.f);
-    qdesc.assign((size_t)qE * 32, 0u);
-    for (int st2 = 0; st2 < 32; ++st2) {
-      const int sl = st2 & 15, t = st2 >> 4;
-      int e = 0;
-      for (int m : streams[st2])
-        for (int g = 0; g < n4[m]; ++g, ++e) {
-          for (int q = 0; q < 4; ++q) {
-            const int k = lo4[m] + 4 * g + q;
-            const bool in = k >= lo[m] && k < lo[m] + cnt[m];
-            qw[((size_t)(e * 2 + t) * 16 + sl) * 4 + q] = in ? 0.25f * mel_dense[(size_t)m * nb + k] : 0.f;
-          }
-          qdesc[((size_t)e * 16 + sl) * 2 + t] =
-              (uint32_t)(lo4[m] / 4 + g) | ((uint32_t)m << 8) | (g == n4[m] - 1 ? 0x10000u : 0u);
-        }
-    }
-  }
-  std::vector<float> qtw2(64, 0.f);
-  for (int typ = 0; typ < 2; ++typ)
-    for (int k = 0; k < 8; ++k) {
-      const double a0 = 2.0 * M_PI * (double)(typ * k) / 32.0, a1 = 2.0 * M_PI * (double)((typ + 2) * k) / 32.0;
-      qtw2[(typ * 8 + k) * 4 + 0] = (float)std::cos(a0);
-      qtw2[(typ * 8 + k) * 4 + 1] = (float)std::sin(a0);
-      qtw2[(typ * 8 + k) * 4 + 2] = (float)std::cos(a1);
-      qtw2[(typ * 8 + k) * 4 + 3] = (float)std::sin(a1);
-    }
-  // ---- tcgen05 DFT-as-GEMM tables (see spl_internal.cuh / fbank_tc.cu) ----
-  const int half = nfft / 4, units = nfft / 32;
-  auto tf32_rn = [](double v) {  // nearest TF32 (10 explicit mantissa bits), returned as float
-    float f = (float)v;
-    uint32_t u;
-    std::memcpy(&u, &f, 4);
-    u += 0xFFFu + ((u >> 13) & 1u);  // round to nearest even on the 13 dropped bits
-    u &= 0xFFFFE000u;
-    std::memcpy(&f, &u, 4);
-    return f;
-  };
-  std::vector<float> tcb((size_t)units * 8 * half * 8);
-  for (int u = 0; u < units; ++u)
-    for (int blk = 0; blk < 4; ++blk)
-      for (int n = 0; n < half; ++n)
-        for (int e = 0; e < 8; ++e) {
-          const int jp = 8 * u + e, j = 2 * jp + (blk & 1), k = n + 1;
-          const double ang = 2.0 * M_PI * (double)((long)j * k % nfft) / (double)nfft;
-          const double v = blk < 2 ? std::cos(ang) : std::sin(ang);
-          const float hi = tf32_rn(v), lo = tf32_rn(v - (double)hi);
-          // SWIZZLE_32B K-major tile of [half x 8]: byte offset r*32 + ((c>>2 ^ r>>2)&1)*16 + (c&3)*4
-          const size_t off = (size_t)(n * 32 + ((((e >> 2) ^ (n >> 2)) & 1) << 4) + ((e & 3) << 2)) / 4;
-          const size_t tile = (size_t)half * 8;
-          tcb[((size_t)u * 8 + blk * 2 + 0) * tile + off] = hi;
-          tcb[((size_t)u * 8 + blk * 2 + 1) * tile + off] = lo;
-        }
-  // mel segments over the split power layout: array 0 index n <-> bin n+1, array 1 index n <-> bin nb-1-n
-  std::vector<float> sw;
-  std::vector<uint32_t> sdesc;  // pairs (x, y)
-  std::vector<int> scost, sfilt;
-  for (int m = 0; m < D; ++m) {
-    struct Run { int arr, i0, i1; };
-    Run runs[2];
-    int nr = 0;
-    if (cnt[m] > 0) {
-      const int b0 = lo[m], b1 = lo[m] + cnt[m] - 1;  // bins (>= 1, <= nb-1)
-      if (b0 <= half) runs[nr++] = {0, (b0 < 1 ? 1 : b0) - 1, (b1 < half ? b1 : half) - 1};
-      if (b1 > half) runs[nr++] = {1, nb - 1 - b1, nb - 1 - (b0 > half + 1 ? b0 : half + 1)};
-    }
-    if (nr == 0) runs[nr++] = {0, 0, -1};  // empty filter: one zero-length segment -> log(eps)
-    for (int r = 0; r < nr; ++r) {
-      int start4 = runs[r].i0 & ~3;
-      int n4 = runs[r].i1 >= runs[r].i0 ? (runs[r].i1 - start4 + 4) / 4 : 0;
-      if (start4 + 4 * n4 > half) start4 = half - 4 * n4;
-      const uint32_t woff4 = (uint32_t)(sw.size() / 4);
-      for (int i = 0; i < 4 * n4; ++i) {
-        const int idx = start4 + i;
-        const int bin = runs[r].arr == 0 ? idx + 1 : nb - 1 - idx;
-        const bool in = idx >= runs[r].i0 && idx <= runs[r].i1 && bin >= lo[m] && bin < lo[m] + cnt[m];
-        sw.push_back(in ? mel_dense[(size_t)m * nb + bin] : 0.f);
-      }
-      sdesc.push_back((uint32_t)(start4 >> 2) | ((uint32_t)n4 << 6) | ((uint32_t)runs[r].arr << 12) |
-                      ((r == 0 ? 1u : 0u) << 13) | ((r == nr - 1 ? 1u : 0u) << 14) | ((uint32_t)m << 16));
-      sdesc.push_back(woff4);
-      scost.push_back(10 + 6 * n4 + (r == nr - 1 ? 8 : 0));
-      sfilt.push_back(m);
-    }
-  }
-  const int nseg = (int)scost.size();
-  int32_t sgrp[5];
-  {
-    long total = 0;
-    for (int i = 0; i < nseg; ++i) total += scost[i];
-    int i = 0;
-    long acc = 0;
-    sgrp[0] = 0;
-    for (int g = 1; g < 4; ++g) {
-      const long target = total * g / 4;
-      while (i < nseg && (acc + scost[i] / 2 < target || (i > 0 && sfilt[i] == sfilt[i - 1]))) acc += scost[i++];
-      sgrp[g] = i;
-    }
-    sgrp[4] = nseg;
-  }
-  // DFT of the window (dither-mean correction): Wc[k] = sum w_j cos, Ws[k] = sum w_j sin, k = 0..nb-1
-  std::vector<float> wc(nb), wsn(nb);
-  for (int k = 0; k < nb; ++k) {
-    double c = 0, s_ = 0;
-    for (int j = 0; j < Nw; ++j) {
-      const double ang = 2.0 * M_PI * (double)((long)j * k % nfft) / (double)nfft;
-      c += (double)window[j] * std::cos(ang);
-      s_ += (double)window[j] * std::sin(ang);
-    }
-    wc[k] = (float)c;
-    wsn[k] = (float)s_;
-  }
-
   // stage-1 twiddles W_N^{n2 k1}
   const int R2 = nfft / 16;
   std::vector<float> twr(R2 * 16), twi(R2 * 16);
@@ -341,54 +170,42 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
 
   DeviceGuard guard(device);
   if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_create: cudaSetDevice failed");
-  // one blob: persistent table block (16-byte aligned, first) | window | tw_re | tw_im | mel_w | lo | cnt | off
+  // one blob: warp-kernel table block (16-byte aligned, first) | window | tw_re | tw_im | mel_w | lo | cnt | off |
+  //           umma tables and twiddle images of both sample formats (16-byte aligned)
   auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
-  const size_t pt_desc = pad4(pw.size()), pt_win = pt_desc + pad4(npairs), pt_tw = pt_win + pad4(Nw);
-  const size_t pt_words = pt_tw + 2 * (size_t)nfft;
   const size_t wt_desc = pad4(ww.size()), wt_jinfo = wt_desc + pad4(wdesc.size()), wt_win = wt_jinfo + pad4(jinfo.size());
   const size_t wt_tw = wt_win + pad4(Nw), wt_words = wt_tw + 2 * (size_t)nfft;
-  const size_t tt_desc = pad4(sw.size()), tt_win = tt_desc + pad4(sdesc.size()), tt_wc = tt_win + pad4(Nw);
-  const size_t tt_ws = tt_wc + pad4(nb), tt_words = tt_ws + pad4(nb);
-  const size_t tcb_words = tcb.size();  // multiple of 4
-  const size_t qt_desc = pad4(qw.size()), qt_win = qt_desc + pad4(qdesc.size()), qt_tw = qt_win + pad4(Nw);
-  const size_t qt_tw2 = qt_tw + 2 * (size_t)nfft, qt_words = qt_tw2 + 64;
-  const size_t n_items = pt_words + wt_words + tt_words + tcb_words + qt_words + (size_t)Nw + 2 * (size_t)R2 * 16 +
-                         (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  spl::UmmaHostTables ut;
+  if (!cfg->use_energy) spl::build_umma_tables(nfft, Nw, D, window, mel_dense, ut);
+  size_t n_items = wt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  n_items = pad4(n_items);
+  size_t o_utab[2] = {0, 0}, o_utw[2] = {0, 0};
+  for (int f = 0; f < 2; ++f) {
+    o_utab[f] = n_items;
+    n_items += pad4(ut.tab[f].size());
+    o_utw[f] = n_items;
+    n_items += pad4(ut.twiddles[f].size() / 4);
+  }
   std::vector<uint32_t> host(n_items, 0u);
-  std::memcpy(host.data(), pw.data(), pw.size() * 4);
-  std::memcpy(host.data() + pt_desc, pdesc.data(), npairs * 4);
-  std::memcpy(host.data() + pt_win, window, Nw * 4);
+  std::vector<float> twt(2 * (size_t)nfft);
   for (int n2 = 0; n2 < R2; ++n2)
     for (int k1 = 0; k1 < 16; ++k1) {  // transposed: conflict-free for lane = n2
-      std::memcpy(host.data() + pt_tw + k1 * R2 + n2, &twr[n2 * 16 + k1], 4);
-      std::memcpy(host.data() + pt_tw + nfft + k1 * R2 + n2, &twi[n2 * 16 + k1], 4);
+      twt[k1 * R2 + n2] = twr[n2 * 16 + k1];
+      twt[nfft + k1 * R2 + n2] = twi[n2 * 16 + k1];
     }
   {
-    uint32_t* wt = host.data() + pt_words;  // pt_words is a multiple of 4: the block stays 16-byte aligned
+    uint32_t* wt = host.data();
     std::memcpy(wt, ww.data(), ww.size() * 4);
     std::memcpy(wt + wt_desc, wdesc.data(), wdesc.size() * 4);
     std::memcpy(wt + wt_jinfo, jinfo.data(), jinfo.size() * 4);
     std::memcpy(wt + wt_win, window, Nw * 4);
-    std::memcpy(wt + wt_tw, host.data() + pt_tw, 2 * (size_t)nfft * 4);
+    std::memcpy(wt + wt_tw, twt.data(), 2 * (size_t)nfft * 4);
   }
-  {
-    uint32_t* tt = host.data() + pt_words + wt_words;
-    std::memcpy(tt, sw.data(), sw.size() * 4);
-    std::memcpy(tt + tt_desc, sdesc.data(), sdesc.size() * 4);
-    std::memcpy(tt + tt_win, window, Nw * 4);
-    std::memcpy(tt + tt_wc, wc.data(), nb * 4);
-    std::memcpy(tt + tt_ws, wsn.data(), nb * 4);
-    std::memcpy(tt + tt_words, tcb.data(), tcb_words * 4);
+  for (int f = 0; f < 2; ++f) {
+    if (!ut.tab[f].empty()) std::memcpy(host.data() + o_utab[f], ut.tab[f].data(), ut.tab[f].size() * 4);
+    if (!ut.twiddles[f].empty()) std::memcpy(host.data() + o_utw[f], ut.twiddles[f].data(), ut.twiddles[f].size());
   }
-  {
-    uint32_t* qt = host.data() + pt_words + wt_words + tt_words + tcb_words;  // all multiples of 4: 16-byte aligned
-    if (!qw.empty()) std::memcpy(qt, qw.data(), qw.size() * 4);
-    if (!qdesc.empty()) std::memcpy(qt + qt_desc, qdesc.data(), qdesc.size() * 4);
-    std::memcpy(qt + qt_win, window, Nw * 4);
-    std::memcpy(qt + qt_tw, host.data() + pt_tw, 2 * (size_t)nfft * 4);
-    std::memcpy(qt + qt_tw2, qtw2.data(), 64 * 4);
-  }
-  size_t o = pt_words + wt_words + tt_words + tcb_words + qt_words;
+  size_t o = wt_words;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -424,58 +241,62 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.mel_off = ib + o_off;
   h->tab.mel_nnz = nnz;
   for (int w = 0; w <= spl::kWarps; ++w) h->tab.grp_beg[w] = grp[w];
-  h->tab.ptab = fb;
-  h->tab.ptab_words = (int32_t)pt_words;
-  h->tab.pt_off_desc = (int32_t)pt_desc;
-  h->tab.pt_off_win = (int32_t)pt_win;
-  h->tab.pt_off_tw = (int32_t)pt_tw;
-  h->tab.npairs = npairs;
-  h->tab.wtab = fb + pt_words;
+  h->tab.wtab = fb;
   h->tab.wtab_words = (int32_t)wt_words;
   h->tab.wt_off_desc = (int32_t)wt_desc;
   h->tab.wt_off_jinfo = (int32_t)wt_jinfo;
   h->tab.wt_off_win = (int32_t)wt_win;
   h->tab.wt_off_tw = (int32_t)wt_tw;
   h->tab.nj = nj;
-  h->tab.tc_tab = fb + pt_words + wt_words;
-  h->tab.tc_b = fb + pt_words + wt_words + tt_words;
-  h->tab.tc_tab_words = (int32_t)tt_words;
-  h->tab.tc_off_desc = (int32_t)tt_desc;
-  h->tab.tc_off_win = (int32_t)tt_win;
-  h->tab.tc_off_wc = (int32_t)tt_wc;
-  h->tab.tc_off_ws = (int32_t)tt_ws;
-  h->tab.tc_nseg = nseg;
-  for (int g = 0; g < 5; ++g) h->tab.tc_sgrp_beg[g] = sgrp[g];
-  h->tab.qtab = fb + pt_words + wt_words + tt_words + tcb_words;
-  h->tab.qtab_words = (int32_t)qt_words;
-  h->tab.qt_off_desc = (int32_t)qt_desc;
-  h->tab.qt_off_win = (int32_t)qt_win;
-  h->tab.qt_off_tw = (int32_t)qt_tw;
-  h->tab.qt_off_tw2 = (int32_t)qt_tw2;
-  h->tab.qE = qE;
-  for (int w = 0; w <= spl::kWarps; ++w) h->tab.pgrp_beg[w] = pgrp[w];
+  h->umma_nflush = ut.nflush;
+  for (int f = 0; f < 2; ++f) {
+    h->umma_ok[f] = ut.ok && !ut.tab[f].empty();
+    h->umma_tab[f] = fb + o_utab[f];
+    h->umma_tw[f] = reinterpret_cast<const uint8_t*>(fb + o_utw[f]);
+    h->umma_tab_bytes[f] = (int)(ut.tab[f].size() * 4);
+    h->umma_off_melw[f] = ut.off_melw[f];
+    h->umma_off_melc[f] = ut.off_melc[f];
+    if (h->umma_ok[f] &&
+        spl::fbank_umma_smem_bytes(nfft, f == 0 ? 4 : 2, h->umma_tab_bytes[f], h->D_out) > 227 * 1024)
+      h->umma_ok[f] = false;
+  }
   h->num_sms = 148;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-  const char* leg = std::getenv("SPL_LEGACY_KERNEL");
-  // 3: tcgen05 DFT-as-GEMM (experimental), 4: pair-pipelined (Nfft = 512)
-  h->kernel = (leg && leg[0] >= '0' && leg[0] <= '4') ? leg[0] - '0' : 0;
-  const char* cps = std::getenv("SPL_CTAS_PER_SM");  // experiment knob: persistent CTAs per SM (1 or 2)
+  // SPL_ENGINE: umma (default: tcgen05 DFT-as-GEMM), fft (warp-pipelined FFT on the fp32x2 pipe), simple (one tile per CTA)
+  const char* eng = std::getenv("SPL_ENGINE");
+  h->engine = ENGINE_UMMA;
+  if (eng && !std::strcmp(eng, "fft")) h->engine = ENGINE_FFT;
+  if (eng && !std::strcmp(eng, "simple")) h->engine = ENGINE_SIMPLE;
+  const char* cps = std::getenv("SPL_CTAS_PER_SM");  // FFT engine knob: 1 = 8-warp CTAs (two launches co-resident per SM)
   h->ctas_per_sm = (cps && cps[0] == '1') ? 1 : 2;
-  h->smem_pair = nfft == 512 ? spl::fbank_pair_smem_bytes(h->D_out, (int)qt_words) : 0;
-  if (h->kernel == 4 && (nfft != 512 || h->smem_pair > 113 * 1024 || S + Nw + 4 > 564)) h->kernel = 0;
   h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 8);
   h->smem_warp16 = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 16);
   {  // the warp kernel stages a group's samples inside one pair's exchange planes
     const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
-    if (h->kernel == 0 && (h->smem_warp > 113 * 1024 || 3 * S + Nw + 4 > 2 * pl)) h->kernel = 2;
+    h->fft_ok = h->smem_warp <= 113 * 1024 && 3 * S + Nw + 4 <= 2 * pl;
   }
   h->smem_bytes = spl::fbank_smem_bytes(nfft, S, Nw, D, h->D_out, nnz);
-  const size_t smem_p = spl::fbank_persistent_smem_bytes(nfft, S, Nw, h->D_out, (int)pt_words);
-  if (smem_p > h->smem_bytes) h->smem_bytes = smem_p;
   if (h->smem_bytes > 113 * 1024) {  // two CTAs per SM must fit in 227 KB
     cudaFree(blob);
     delete h;
     return fail(SPL_ERR_UNSUPPORTED, "spl_create: configuration needs too much shared memory");
+  }
+  h->status = nullptr;
+  e = cudaMalloc(reinterpret_cast<void**>(&h->status), 256);
+  if (e == cudaSuccess) e = cudaMemset(h->status, 0, 256);
+  if (e != cudaSuccess) {
+    cudaFree(blob);
+    delete h;
+    return fail_cuda(e, "spl_create: status word");
+  }
+  h->umma_ctas = h->num_sms;
+  if (const char* uc = std::getenv("SPL_UMMA_CTAS"); uc && std::atoi(uc) > 0) h->umma_ctas = std::atoi(uc);
+  h->debug_acc = nullptr;
+  if (const char* dbg = std::getenv("SPL_UMMA_DEBUG"); dbg && dbg[0] == '1') {
+    if (cudaMalloc(reinterpret_cast<void**>(&h->debug_acc), 128 * 513 * sizeof(float)) == cudaSuccess)
+      cudaMemset(h->debug_acc, 0, 128 * 513 * sizeof(float));
+    else
+      h->debug_acc = nullptr;
   }
   *out = h;
   return SPL_OK;
@@ -485,21 +306,39 @@ void spl_destroy(spl_handle* h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   cudaFree(h->blob);
+  cudaFree(h->status);
+  cudaFree(h->debug_acc);
   delete h;
 }
 
-int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
-  if (!h || !a) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null argument");
-  if (!a->wav || !a->wav_len || !a->feats) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null buffer");
-  if (a->B < 1 || a->B > 65535 || a->T < 1) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: B/T out of range");
-  if (a->wav_cols < h->cfg.window_size || a->wav_pitch < a->wav_cols)
-    return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: need window_size <= wav_cols <= wav_pitch");
-  if (a->sample_format != SPL_SAMPLES_F32 && a->sample_format != SPL_SAMPLES_I16)
-    return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: sample_format");
-  DeviceGuard guard(h->device);
-  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_fbank_forward: cudaSetDevice failed");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// ---- kernel A dispatch --------------------------------------------------------------------------------
+namespace {
 
+int check_fbank_args(const spl_handle* h, const spl_fbank_args* a, const char* who) {
+  if (!a->wav || !a->wav_len || !a->feats) return fail(SPL_ERR_INVALID_ARG, std::string(who) + ": null buffer");
+  if (a->B < 1 || a->B > (1 << 22) || a->T < 1) return fail(SPL_ERR_INVALID_ARG, std::string(who) + ": B/T out of range");
+  if (a->wav_cols < h->cfg.window_size || a->wav_pitch < a->wav_cols)
+    return fail(SPL_ERR_INVALID_ARG, std::string(who) + ": need window_size <= wav_cols <= wav_pitch");
+  if (a->sample_format != SPL_SAMPLES_F32 && a->sample_format != SPL_SAMPLES_I16)
+    return fail(SPL_ERR_INVALID_ARG, std::string(who) + ": sample_format");
+  return SPL_OK;
+}
+
+// utterances [b0, b0 + nB) of a batch as a batch of their own (utterances are independent)
+spl_fbank_args slice_batch(const spl_handle* h, const spl_fbank_args& a, int b0, int nB) {
+  spl_fbank_args s = a;
+  const size_t es = a.sample_format == SPL_SAMPLES_F32 ? 4 : 2;
+  s.wav = static_cast<const char*>(a.wav) + (size_t)b0 * a.wav_pitch * es;
+  s.wav_len = a.wav_len + b0;
+  s.B = nB;
+  s.feats = a.feats + (size_t)b0 * a.T * h->D_out;
+  s.feat_len = a.feat_len ? a.feat_len + b0 : nullptr;
+  s.noise = a.noise ? a.noise + (size_t)b0 * a.T * h->cfg.window_size : nullptr;
+  s.utt_stats = a.utt_stats ? a.utt_stats + (size_t)b0 * 2 * h->D_out : nullptr;
+  return s;
+}
+
+cudaError_t launch_one_fft(spl_handle* h, const spl_fbank_args& a, cudaStream_t st, bool simple) {
   spl::FbankParams p;
   p.S = h->cfg.window_shift;
   p.Nw = h->cfg.window_size;
@@ -509,48 +348,180 @@ int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
   p.remove_dc = h->cfg.remove_dc;
   p.preemph = h->cfg.preemph;
   p.dither = h->cfg.dither;
-  p.wav = a->wav;
-  p.wav_pitch = a->wav_pitch;
-  p.wav_cols = a->wav_cols;
-  p.sample_format = a->sample_format;
-  p.wav_len = a->wav_len;
-  p.B = a->B;
-  p.T = a->T;
-  p.feats = a->feats;
-  p.feat_len = a->feat_len;
-  p.noise = a->noise;
-  p.seed_lo = (uint32_t)(a->dither_seed & 0xffffffffu);
-  p.seed_hi = (uint32_t)(a->dither_seed >> 32);
-  p.utt_stats = a->utt_stats;
-  p.global_stats = a->global_stats;
+  p.wav = a.wav;
+  p.wav_pitch = a.wav_pitch;
+  p.wav_cols = a.wav_cols;
+  p.sample_format = a.sample_format;
+  p.wav_len = a.wav_len;
+  p.B = a.B;
+  p.T = a.T;
+  p.feats = a.feats;
+  p.feat_len = a.feat_len;
+  p.noise = a.noise;
+  p.seed_lo = (uint32_t)(a.dither_seed & 0xffffffffu);
+  p.seed_hi = (uint32_t)(a.dither_seed >> 32);
+  p.utt_stats = a.utt_stats;
+  p.global_stats = a.global_stats;
   p.tab = h->tab;
-
-  if (a->utt_stats) {
-    cudaError_t e = cudaMemsetAsync(a->utt_stats, 0, sizeof(double) * 2 * (size_t)a->B * h->D_out, st);
-    if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: cudaMemsetAsync");
-  }
   const bool with_noise = h->cfg.dither != 0.f;
-  cudaError_t e;
-  if (h->kernel == 3 && a->B <= spl::kMaxPersistentB && a->sample_format == SPL_SAMPLES_F32 && h->cfg.dither == 0.f &&
-      h->cfg.window_size * 2 > h->cfg.padded_size)
-    e = spl::launch_fbank_tc(p, h->cfg.padded_size, with_noise, h->num_sms, st);
-  else if (h->kernel == 4 && a->B <= spl::kMaxPersistentB)
-    e = spl::launch_fbank_pair(p, with_noise, h->ctas_per_sm * h->num_sms, st);
-  else if ((h->kernel == 0 || h->kernel == 3 || h->kernel == 4) && a->B <= spl::kMaxPersistentB)
-    {
-    // default: one 16-warp CTA per SM; SPL_CTAS_PER_SM=1 (throughput mode) or a table block too large for
-    // 227 KB: 8-warp CTAs
-    const bool wide = h->ctas_per_sm == 2 && h->smem_warp16 <= 227 * 1024;
-    e = spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, wide ? 16 : 8,
-                               wide ? h->num_sms : h->ctas_per_sm * h->num_sms, st);
+  if (simple) return spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
+  // one 16-warp CTA per SM; SPL_CTAS_PER_SM=1 (throughput mode) or a table block too large for 227 KB: 8-warp CTAs
+  const bool wide = h->ctas_per_sm == 2 && h->smem_warp16 <= 227 * 1024;
+  return spl::launch_fbank_warp(p, h->cfg.padded_size, with_noise, wide ? 16 : 8,
+                                wide ? h->num_sms : h->ctas_per_sm * h->num_sms, st);
+}
+
+// every batch of `v` shares sample format / noise mode; <= kMaxBatches batches, <= kMaxUmmaUtts utterances
+cudaError_t launch_umma(spl_handle* h, const spl_fbank_args* v, int n, cudaStream_t st) {
+  const int f = v[0].sample_format == SPL_SAMPLES_F32 ? 0 : 1;
+  spl::UmmaParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.S = h->cfg.window_shift;
+  p.Nw = h->cfg.window_size;
+  p.D_out = h->D_out;
+  p.remove_dc = h->cfg.remove_dc;
+  p.preemph = h->cfg.preemph;
+  p.dither = h->cfg.dither;
+  p.seed_lo = (uint32_t)(v[0].dither_seed & 0xffffffffu);
+  p.seed_hi = (uint32_t)(v[0].dither_seed >> 32);
+  p.nb = n;
+  p.nflush = h->umma_nflush;
+  p.global_stats = v[0].global_stats;
+  p.status = h->status;
+  p.debug_acc = h->debug_acc;
+  p.twiddles = h->umma_tw[f];
+  p.tab = h->umma_tab[f];
+  p.tab_bytes = h->umma_tab_bytes[f];
+  p.off_melw = h->umma_off_melw[f];
+  p.off_melc = h->umma_off_melc[f];
+  int u0 = 0;
+  for (int k = 0; k < n; ++k) {
+    spl::UBatch& b = p.bd[k];
+    b.wav = v[k].wav;
+    b.wav_len = v[k].wav_len;
+    b.feats = v[k].feats;
+    b.feat_len = v[k].feat_len;
+    b.noise = v[k].noise;
+    b.utt_stats = v[k].utt_stats;
+    b.wav_pitch = v[k].wav_pitch;
+    b.wav_cols = v[k].wav_cols;
+    b.B = v[k].B;
+    b.T = v[k].T;
+    b.u0 = u0;
+    u0 += v[k].B;
+    if (v[k].utt_stats) p.want_utt_stats = 1;
   }
-  else if (h->kernel == 2 && a->B <= spl::kMaxPersistentB)
-    e = spl::launch_fbank_persistent(p, h->cfg.padded_size, with_noise, 2 * h->num_sms, st);
-  else
-    e = spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
-  if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: launch");
-  g_launches.fetch_add(1);
+  p.total_utts = u0;
+  const int noise_mode = h->cfg.dither == 0.f ? 0 : (v[0].noise ? 2 : 1);
+  return spl::launch_fbank_umma(p, h->cfg.padded_size, v[0].sample_format, noise_mode, h->umma_ctas, st);
+}
+
+}  // namespace
+
+int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n, void* stream) {
+  if (!h || !args || n < 1) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward_multi: null argument");
+  for (int i = 0; i < n; ++i) {
+    const int rc = check_fbank_args(h, args + i, "spl_fbank_forward");
+    if (rc != SPL_OK) return rc;
+  }
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_fbank_forward: cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // zero the per-utterance sums (contiguous buffers of consecutive batches share one memset)
+  for (int i = 0; i < n;) {
+    if (!args[i].utt_stats) {
+      ++i;
+      continue;
+    }
+    double* beg = args[i].utt_stats;
+    double* end = beg + 2 * (size_t)args[i].B * h->D_out;
+    int j = i + 1;
+    while (j < n && args[j].utt_stats == end) {
+      end += 2 * (size_t)args[j].B * h->D_out;
+      ++j;
+    }
+    cudaError_t e = cudaMemsetAsync(beg, 0, (size_t)(end - beg) * sizeof(double), st);
+    if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: cudaMemsetAsync");
+    i = j;
+  }
+
+  // split into launches: pieces of <= kMaxUmmaUtts utterances; the tcgen05 engine takes up to kMaxBatches pieces
+  // (same sample format / noise mode / global_stats target) per launch, the FFT engines one piece per launch
+  std::vector<spl_fbank_args> pieces;
+  for (int i = 0; i < n; ++i)
+    for (int b0 = 0; b0 < args[i].B; b0 += spl::kMaxUmmaUtts)
+      pieces.push_back(slice_batch(h, args[i], b0, std::min<int>(spl::kMaxUmmaUtts, args[i].B - b0)));
+  size_t i = 0;
+  while (i < pieces.size()) {
+    const spl_fbank_args& a = pieces[i];
+    const int f = a.sample_format == SPL_SAMPLES_F32 ? 0 : 1;
+    const bool umma = h->engine == ENGINE_UMMA && h->umma_ok[f];
+    cudaError_t e;
+    if (umma) {
+      size_t j = i + 1;
+      int utts = a.B;
+      while (j < pieces.size() && j - i < (size_t)spl::kMaxBatches && utts + pieces[j].B <= spl::kMaxUmmaUtts &&
+             pieces[j].sample_format == a.sample_format && (pieces[j].noise != nullptr) == (a.noise != nullptr) &&
+             pieces[j].global_stats == a.global_stats) {
+        utts += pieces[j].B;
+        ++j;
+      }
+      e = launch_umma(h, pieces.data() + i, (int)(j - i), st);
+      i = j;
+    } else {
+      e = launch_one_fft(h, a, st, h->engine == ENGINE_SIMPLE || !h->fft_ok);
+      ++i;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: launch");
+    g_launches.fetch_add(1);
+  }
   return SPL_OK;
+}
+
+int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stream) {
+  if (!h || !a) return fail(SPL_ERR_INVALID_ARG, "spl_fbank_forward: null argument");
+  return spl_fbank_forward_multi(h, a, 1, stream);
+}
+
+int spl_debug_status(spl_handle* h) {
+  if (!h) return -1;
+  DeviceGuard guard(h->device);
+  int32_t v = -1;
+  if (cudaMemcpy(&v, h->status, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
+
+int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* window, const float* mel_dense, int32_t fmt,
+                          void* twiddles, size_t twiddle_cap, float* tab, size_t tab_cap, int32_t* info) {
+  if (!window || !mel_dense || !info || fmt < 0 || fmt > 1) return fail(SPL_ERR_INVALID_ARG, "spl_debug_umma_tables: bad argument");
+  spl::UmmaHostTables ut;
+  spl::build_umma_tables(nfft, Nw, D, window, mel_dense, ut);
+  info[0] = ut.ok && !ut.tab[fmt].empty();
+  info[1] = (int32_t)ut.twiddles[fmt].size();
+  info[2] = (int32_t)ut.tab[fmt].size();
+  info[3] = ut.off_melw[fmt];
+  info[4] = ut.off_melc[fmt];
+  info[5] = ut.nflush;
+  if (!info[0]) return SPL_OK;
+  if (twiddles && twiddle_cap >= ut.twiddles[fmt].size()) std::memcpy(twiddles, ut.twiddles[fmt].data(), ut.twiddles[fmt].size());
+  if (tab && tab_cap >= ut.tab[fmt].size()) std::memcpy(tab, ut.tab[fmt].data(), ut.tab[fmt].size() * 4);
+  return SPL_OK;
+}
+
+int spl_debug_umma_acc(spl_handle* h, float* host_out, size_t n_floats) {
+  if (!h || !h->debug_acc || !host_out) return fail(SPL_ERR_INVALID_ARG, "spl_debug_umma_acc: needs SPL_UMMA_DEBUG=1 at spl_create");
+  DeviceGuard guard(h->device);
+  const size_t n = std::min<size_t>(n_floats, 128 * 513);
+  cudaError_t e = cudaMemcpy(host_out, h->debug_acc, n * sizeof(float), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? SPL_OK : fail_cuda(e, "spl_debug_umma_acc");
+}
+
+const char* spl_engine_name(const spl_handle* h, int32_t sample_format) {
+  if (!h) return "";
+  const int f = sample_format == SPL_SAMPLES_F32 ? 0 : 1;
+  if (h->engine == ENGINE_UMMA && h->umma_ok[f]) return "umma";
+  return (h->engine == ENGINE_SIMPLE || !h->fft_ok) ? "simple" : "fft";
 }
 
 int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream) {

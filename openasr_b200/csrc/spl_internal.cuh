@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/spl_capi.h"
 
 namespace spl {
@@ -26,17 +28,6 @@ struct Tables {
   const int32_t* mel_off;  // [D] offset into mel_w
   int32_t mel_nnz;
   int32_t grp_beg[kWarps + 1];  // filters [grp_beg[w], grp_beg[w+1]) handled by warp w in the mel phase
-  // persistent kernel: ONE contiguous block that is bulk-copied (TMA) into shared memory as is:
-  //   [pair weights | pair descriptors | window | stage-1 twiddles, transposed]
-  // Filters are processed two at a time; every pair is padded (zero weights) to a common number of
-  // 16-byte aligned 4-bin groups kept inside [0, Nfft/2).
-  //   weights     : for pair i, group g: 8 floats {wa[4], wb[4]}
-  //   descriptors : loA/4 | loB/4 << 6 | n4 << 12 | (weight offset / 8) << 18 | validB << 31
-  const float* ptab;
-  int32_t ptab_words;           // total 4-byte words, multiple of 4
-  int32_t pt_off_desc, pt_off_win, pt_off_tw;  // word offsets inside the block
-  int32_t npairs;
-  int32_t pgrp_beg[kWarps + 1]; // pairs [pgrp_beg[w], pgrp_beg[w+1]) handled by warp w in the mel phase
   // warp-pipelined kernel: mel phase with lane = (frame f = lane & 3, slice s = lane >> 2); in
   // iteration j slice s handles filter pair 8 j + s, all eight pairs padded to n4j groups.
   //   [weights: float4 index ((goff_j + g) * 2 + half) * 8 + s | pair descriptors (8 per j):
@@ -45,24 +36,6 @@ struct Tables {
   int32_t wtab_words;
   int32_t wt_off_desc, wt_off_jinfo, wt_off_win, wt_off_tw;
   int32_t nj;
-  // tcgen05 DFT-as-GEMM kernel (fbank_tc.cu).  HALF = Nfft/4 outputs / inputs per folded block.
-  //   tc_b   : twiddle operand images, [Nfft/32 units][4 blocks: cos-even, cos-odd, sin-even, sin-odd]
-  //            [hi, lo][HALF n x 8 k tf32, K-major SWIZZLE_32B] -- copied to shared memory verbatim
-  //   tc_tab : [segment weights | segment descriptors (uint2) | window | Wc | Ws], one TMA bulk copy
-  //   segment descriptor .x: start/4 | n4 << 6 | array (0: bins 1..HALF, 1: mirrored bins) << 12 |
-  //            first << 13 | last << 14 | filter << 16 ;  .y: weight offset / 4
-  const float* tc_b;
-  const float* tc_tab;
-  int32_t tc_tab_words, tc_off_desc, tc_off_win, tc_off_wc, tc_off_ws;
-  int32_t tc_nseg;
-  int32_t tc_sgrp_beg[5];
-  // pair-pipelined kernel (fbank_pair.cu, Nfft = 512): mel phase with lane = (frame f = lane & 1,
-  // slice s = lane >> 1) and two filter streams t per slice; stream (s, t) walks qE flat entries.
-  //   [weights: float4 index (e * 2 + t) * 16 + s | entry descriptors: uint2 (t = 0, t = 1) at e * 16 + s,
-  //    each  bin/4 | filter << 8 | last-of-filter << 16 | window | stage-1 twiddles^T |
-  //    stage-2 twiddles: float4 {cos, sin (a = typ), cos, sin (a = typ + 2)} of 2 pi a k / 32 at typ * 8 + k]
-  const float* qtab;
-  int32_t qtab_words, qt_off_desc, qt_off_win, qt_off_tw, qt_off_tw2, qE;
 };
 
 struct FbankParams {
@@ -99,16 +72,10 @@ struct PostParams {
 // host-side launchers (defined in the .cu files); return cudaError_t of the launch
 cudaError_t launch_fbank(const FbankParams& p, int nfft, bool with_noise, cudaStream_t st);
 size_t fbank_smem_bytes(int nfft, int S, int Nw, int D, int D_out, int nnz);
-// persistent, load-balanced kernel (B <= kMaxPersistentB); num_ctas = 2 * SM count
-constexpr int kMaxPersistentB = 512;
-cudaError_t launch_fbank_persistent(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
-size_t fbank_persistent_smem_bytes(int nfft, int S, int Nw, int D_out, int ptab_words);
+constexpr int kMaxPersistentB = 512;  // utterances per launch of the warp-pipelined kernel (prefix tables in shared memory)
 // warp-pipelined kernel: one CTA of 16 independent warps per SM, no block-wide barriers in the loop
 cudaError_t launch_fbank_warp(const FbankParams& p, int nfft, bool with_noise, int warps, int num_ctas, cudaStream_t st);
 size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words, int warps);
-// pair-pipelined kernel (Nfft = 512 only): 2 CTAs x 12 warps per SM, one packed pair per warp iteration
-cudaError_t launch_fbank_pair(const FbankParams& p, bool with_noise, int num_ctas, cudaStream_t st);
-size_t fbank_pair_smem_bytes(int D_out, int qtab_words);
 cudaError_t launch_post(const PostParams& p, cudaStream_t st);
 cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int B, int T, int Dm,
                                 double* utt_stats, cudaStream_t st);
@@ -117,9 +84,50 @@ cudaError_t launch_column_stats(const float* feats, const int64_t* feat_len, int
 cudaError_t launch_conv0_relu(const float* x, const float* w, const float* bias, float* out, int B, int T, int D, int C,
                               cudaStream_t st);
 
-// tcgen05 DFT-as-GEMM fbank kernel (fp32 samples, B <= kMaxPersistentB); one CTA per SM
-cudaError_t launch_fbank_tc(const FbankParams& p, int nfft, bool with_noise, int num_ctas, cudaStream_t st);
-size_t fbank_tc_smem_bytes(int nfft, int D_out, int tc_tab_words);
+// ---------------------------------------------------------------------------------------------
+// tcgen05 DFT-as-GEMM engine (fbank_umma.cu): persistent, multi-batch
+constexpr int kMaxBatches = 8;      // batches per launch
+constexpr int kMaxUmmaUtts = 512;   // flattened utterances per launch (frame prefix table in shared memory)
+
+struct UBatch {  // one padded batch of a (multi-)call; device pointers
+  const void* wav;
+  const int64_t* wav_len;
+  float* feats;
+  int64_t* feat_len;
+  const float* noise;
+  double* utt_stats;
+  int64_t wav_pitch, wav_cols;
+  int32_t B, T;
+  int32_t u0;    // index of the batch's first utterance in the flattened list
+  int32_t pad_;
+};
+
+struct UmmaParams {
+  int32_t S, Nw, D_out, remove_dc;
+  float preemph, dither;
+  uint32_t seed_lo, seed_hi;
+  int32_t nb, total_utts, nflush, want_utt_stats;
+  double* global_stats;
+  int32_t* status;          // device word: 0x10000 | barrier | warp << 8 of the first barrier wait that timed out
+  float* debug_acc;         // diagnostics: raw accumulators of tile 0 of CTA 0, [128][4 HALF + 1], or NULL
+  const uint8_t* twiddles;  // [(Nfft/64 + 1) chunks][cos | sin half][4 tiles of HALF x 16 FP16, SWIZZLE_32B]
+  const float* tab;         // [delayed windows: shifts x Nfft | mel steps: float2 (w_a, w_b) x Nfft/2 | shift codes]
+  int32_t tab_bytes, off_melw, off_melc, pad_;
+  UBatch bd[kMaxBatches];
+};
+
+cudaError_t launch_fbank_umma(const UmmaParams& p, int nfft, int sample_format, int noise_mode, int num_ctas, cudaStream_t st);
+size_t fbank_umma_smem_bytes(int nfft, int es, int tab_bytes, int D_out);
+
+// Host-built tables of the engine (umma_tables.cu); `ok == false`: the configuration is outside the engine's domain
+struct UmmaHostTables {
+  bool ok = false;
+  int nflush = 0;
+  int off_melw[2] = {0, 0}, off_melc[2] = {0, 0};  // float offsets inside tab[fmt]
+  std::vector<uint8_t> twiddles[2];  // [0] fp32 samples (4 shifts), [1] int16 samples (8 shifts)
+  std::vector<float> tab[2];
+};
+void build_umma_tables(int nfft, int Nw, int D, const float* window, const float* mel_dense, UmmaHostTables& out);
 
 // tcgen05 building-block self-test (tc_selftest.cu)
 cudaError_t launch_tc_selftest_sw32(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);

@@ -62,7 +62,59 @@ class FbankHandle:
         except Exception:
             pass
 
+    def engine_name(self, dtype=torch.float32) -> str:
+        """Kernel-A engine calls with this sample dtype run on: 'umma' (tcgen05), 'fft' or 'simple'."""
+        fmt = _capi.SAMPLES_F32 if dtype == torch.float32 else _capi.SAMPLES_I16
+        return self._lib.spl_engine_name(self._h, fmt).decode()
+
+    def debug_status(self) -> int:
+        """SYNCHRONOUS: non-zero if a kernel of this handle gave up on an internal barrier (tests only)."""
+        return int(self._lib.spl_debug_status(self._h))
+
     # ------------------------------------------------------------------ kernel A
+    def _fill_args(self, a, wav, wav_len_dev, T, noise, dither_seed, utt_stats, global_stats, out, feat_len):
+        _require_cuda(wav, "wav_batch")
+        if wav.dim() != 2:
+            raise ValueError("wav_batch must be [B, L]")
+        if wav.dtype == torch.float32:
+            fmt = _capi.SAMPLES_F32
+        elif wav.dtype == torch.int16:
+            fmt = _capi.SAMPLES_I16
+        else:
+            raise TypeError("wav_batch must be float32 or int16, got %s" % wav.dtype)
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        B = wav.shape[0]
+        a.wav = wav.data_ptr()
+        a.wav_pitch = wav.stride(0) if B > 1 else wav.shape[1]
+        a.wav_cols = wav.shape[1]
+        a.sample_format = fmt
+        a.wav_len = wav_len_dev if isinstance(wav_len_dev, int) else wav_len_dev.data_ptr()
+        a.B = B
+        a.T = T
+        a.feats = out.data_ptr()
+        a.feat_len = feat_len.data_ptr()
+        a.noise = noise.data_ptr() if noise is not None else None
+        a.dither_seed = dither_seed & 0xFFFFFFFFFFFFFFFF
+        a.utt_stats = utt_stats.data_ptr() if utt_stats is not None else None
+        a.global_stats = global_stats.data_ptr() if global_stats is not None else None
+        return wav  # keeps a contiguous copy alive
+
+    def fbank_multi(self, items, *, dither_seed: int = 0, global_stats: Optional[torch.Tensor] = None,
+                    stream_ptr: Optional[C.c_void_p] = None) -> None:
+        """Several batches in ONE launch of kernel A (spl_fbank_forward_multi).  ``items``: dicts with
+        wav [B, L], lens (device int64), T, feats [B, T, D_out], flen [B] and optionally stats [B, 2, D_out],
+        noise [B, T, Nw]; all on this handle's device, every output pre-allocated by the caller."""
+        n = len(items)
+        arr = (_capi.SplFbankArgs * n)()
+        keep = []
+        for a, it in zip(arr, items):
+            keep.append(self._fill_args(a, it["wav"], it["lens"], it["T"], it.get("noise"), dither_seed,
+                                        it.get("stats"), global_stats, it["feats"], it["flen"]))
+        dev = items[0]["wav"].device
+        _capi.check(self._lib.spl_fbank_forward_multi(self._h, arr, n, stream_ptr or _stream_ptr(dev)),
+                    "spl_fbank_forward_multi")
+
     def fbank(self, wav: torch.Tensor, wav_len_dev: torch.Tensor, T: int, *,
               noise: Optional[torch.Tensor] = None, dither_seed: int = 0,
               utt_stats: Optional[torch.Tensor] = None, global_stats: Optional[torch.Tensor] = None,
@@ -110,7 +162,8 @@ def get_handle(device: torch.device, sample_rate: float, num_mel_bins: int, use_
     """Handle cache keyed by (device, config); safe under DataParallel's per-GPU threads."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     key = (idx, float(sample_rate), int(num_mel_bins), bool(use_energy), float(dither), str(window_type),
-           os.environ.get("SPL_LEGACY_KERNEL", ""), os.environ.get("SPL_CTAS_PER_SM", ""))  # the library reads the switch at spl_create
+           os.environ.get("SPL_ENGINE", ""), os.environ.get("SPL_CTAS_PER_SM", ""),
+           os.environ.get("SPL_UMMA_DEBUG", ""), os.environ.get("SPL_UMMA_CTAS", ""))  # the library reads the switches at spl_create
     with _handles_lock:
         h = _handles.get(key)
         if h is None:

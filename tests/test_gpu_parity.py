@@ -284,25 +284,35 @@ def test_errors_and_api():
 
 
 # --------------------------------------------------------------------------------------------- scheduling edges
-def test_persistent_kernel_matches_simple_kernel(monkeypatch, wavs):
-    """The warp-pipelined and the persistent kernels (TMA staging, balanced group / frame ranges)
-    against the simple one-tile-per-CTA kernel on ragged batches, misaligned rows and storage offsets."""
+def test_engines_agree_on_ragged_misaligned_batches(monkeypatch, wavs):
+    """The three kernel-A engines -- tcgen05 DFT-as-GEMM (default), warp-pipelined FFT, simple one-tile-per-CTA --
+    on ragged batches, misaligned rows (every 16-byte shift) and storage offsets."""
     x, lens = fo.synth_batch(9, 500, 70000, 16000, seed=4)
     x = torch.cat([x, torch.zeros(9, 3)], dim=1)          # odd row pitch -> unaligned rows
     outs = {}
-    # 0 warp-pipelined, 1 simple one-tile-per-CTA, 2 persistent CTA tiles, 4 pair-pipelined
-    for mode in ("0", "1", "2", "4"):
-        monkeypatch.setenv("SPL_LEGACY_KERNEL", mode)
-        layer, conf = make_layer(use_energy=True)
+    for mode in ("umma", "fft", "simple"):
+        monkeypatch.setenv("SPL_ENGINE", mode)
+        layer, conf = make_layer()
         layer.eval()
+        assert layer._handle(torch.device("cuda", 0)).engine_name() == mode
         xc = x.cuda()
-        outs[mode] = (layer(xc, lens)[0], layer(xc[:, 1:], (lens - 1).clamp_min(400))[0])
-    for other in ("0", "2", "4"):  # different rounding order only (fma forms): well inside the tolerance
-        for a, b in zip(outs[other], outs["1"]):
-            assert (a - b).abs().max().item() < 2e-3 and (a - b).abs().mean().item() < 1e-5
-    assert torch.equal(outs["0"][0] == 0, outs["1"][0] == 0)
+        outs[mode] = [layer(xc, lens)[0]] + [layer(xc[:, k:], (lens - k).clamp_min(400))[0] for k in (1, 2, 3)]
+        assert layer._handle(torch.device("cuda", 0)).debug_status() == 0
+    for other in ("umma", "fft"):  # different formulation / rounding order only: well inside the tolerance
+        for a, b in zip(outs[other], outs["simple"]):
+            assert (a - b).abs().max().item() < 2e-3 and (a - b).abs().mean().item() < 2e-5
+    assert torch.equal(outs["umma"][0] == 0, outs["simple"][0] == 0)
     ref, _ = fo.splayer_forward(x, lens.tolist(), conf)
-    close(outs["0"][0], ref, fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)[0])
+    ref64 = fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)[0]
+    close(outs["umma"][0], ref, ref64)
+    close(outs["fft"][0], ref, ref64)
+    # use_energy: the tcgen05 engine hands the configuration to the FFT engine
+    monkeypatch.setenv("SPL_ENGINE", "umma")
+    layer, conf = make_layer(use_energy=True)
+    layer.eval()
+    assert layer._handle(torch.device("cuda", 0)).engine_name() == "fft"
+    close(layer(x.cuda(), lens)[0], fo.splayer_forward(x, lens.tolist(), conf)[0],
+          fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)[0])
 
 
 def test_many_short_utterances_and_large_batches():
@@ -539,9 +549,9 @@ def test_other_sample_rates_generic_window(sr, monkeypatch):
     x = (1800.0 * torch.randn(B, int(lens.max()), generator=g)).round()
     x = x * (torch.arange(x.shape[1])[None, :] < lens[:, None])
     outs = {}
-    for mode in ("0", "1", "2"):
-        monkeypatch.setenv("SPL_LEGACY_KERNEL", mode)
-        layer, conf = make_layer(sample_rate=sr, num_mel_bins=40, use_energy=True)
+    for mode in ("umma", "fft", "simple"):
+        monkeypatch.setenv("SPL_ENGINE", mode)
+        layer, conf = make_layer(sample_rate=sr, num_mel_bins=40)
         layer.eval()
         outs[mode], flen = layer(x.cuda(), lens)
     ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
@@ -550,7 +560,7 @@ def test_other_sample_rates_generic_window(sr, monkeypatch):
     for mode in outs:
         close(outs[mode], ref, ref64)
     # host-stream dither (parity mode) on the generic path
-    monkeypatch.setenv("SPL_LEGACY_KERNEL", "0")
+    monkeypatch.delenv("SPL_ENGINE")
     layer, conf = make_layer(sample_rate=sr, num_mel_bins=40, dither=1.0, dither_rng="host")
     layer.eval()
     torch.manual_seed(5)

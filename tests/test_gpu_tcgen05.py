@@ -42,17 +42,19 @@ def _pad_batch(ws):
 
 @pytest.mark.parametrize("sr,D,energy", [(16000, 80, False), (16000, 40, True), (8000, 40, False)])
 def test_tcgen05_dft_kernel_matches_oracle(monkeypatch, wavs, sr, D, energy):
-    """The DFT-as-GEMM variant of kernel A (3xTF32 on tcgen05, SPL_LEGACY_KERNEL=3) on real speech:
+    """The DFT-as-GEMM engine of kernel A (FP16 hi/lo split on tcgen05, the default engine) on real speech:
     same tolerance as the FFT kernels (|d| <= 1e-3 + 1e-4 |ref|), exact lengths and zero padding."""
     from oracle import frontend_oracle as fo
     from openasr_b200 import SPLayer
-    monkeypatch.setenv("SPL_LEGACY_KERNEL", "3")
+    monkeypatch.setenv("SPL_ENGINE", "umma")
     dec = 16000 // sr
     x, lens = _pad_batch([wavs[0][::dec].contiguous(), wavs[1][::dec].contiguous(), wavs[0][::dec][:7001].contiguous()])
     conf = {"feature_type": "fbank", "sample_rate": sr, "num_mel_bins": D, "use_energy": energy, "dither": 0.0}
     layer = SPLayer(conf).cuda().eval()
+    assert layer._handle(torch.device("cuda", 0)).engine_name() == ("fft" if energy else "umma")
     feats, flen = layer(x.cuda(), lens)
     torch.cuda.synchronize()
+    assert layer._handle(torch.device("cuda", 0)).debug_status() == 0
     ref, rlen = fo.splayer_forward(x, lens, conf)
     ref64, _ = fo.splayer_forward(x, lens, conf, dtype=torch.float64)
     assert torch.equal(flen.cpu(), rlen)
