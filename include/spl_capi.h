@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 1
+#define SPL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SPL_API __attribute__((visibility("default")))
@@ -118,12 +118,26 @@ typedef struct spl_post_args {
   const float* global_mean;  /* [Dm] (global CMVN) or NULL */
   const float* global_istd;  /* [Dm] 1/std (global CMVN) or NULL */
   int32_t n_freq_masks, n_time_masks;
-  const int32_t* mask_params; /* [B, n_freq+n_time, 2] (start, end) half-open, host-drawn; NULL = no SpecAug */
+  const int32_t* mask_params; /* [B, n_freq+n_time, 2] (start, end) half-open, host-drawn; NULL = no SpecAug
+                                 unless mask_uniforms is given */
+  /* Sync-free alternative to mask_params: the 2*(n_freq+n_time) x B uniforms in the reference's draw order
+   * (sp_layers.py:58-71; row 2j = width draw, row 2j+1 = start draw of mask j).  The kernel resolves them against
+   * the DEVICE feat_len with the reference's float32 arithmetic and Python slice semantics -- bit-identical to
+   * spl_specaug_rects -- so the host never needs the frame counts. */
+  const float* mask_uniforms;
+  float freq_mask_width, time_mask_width; /* W_f, W_t (used with mask_uniforms) */
 } spl_post_args;
 
 /* `h` may be NULL for spl_post_inplace / spl_column_stats (offline-feature mode has no fbank
  * handle): the current CUDA device is used. */
 SPL_API int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream);
+/* Kernel B over several batches in one launch (same Dm, CMVN mode, mask counts / widths and global tables, taken
+ * from args[0]; per-batch buffers, B, T).  Up to 8 batches per launch; larger calls are split. */
+SPL_API int spl_post_inplace_multi(spl_handle* h, const spl_post_args* args, int32_t n, void* stream);
+/* The whole SPLayer.forward device work in ONE call: kernel A over `n` batches (spl_fbank_forward_multi) followed by
+ * kernel B over the same batches (post[i].feats / feat_len / utt_stats / B / T / Dm default to fbank[i]'s when 0).
+ * post == NULL: kernel A only. */
+SPL_API int spl_forward_multi(spl_handle* h, const spl_fbank_args* fbank, const spl_post_args* post, int32_t n, void* stream);
 
 /* Per-utterance column sums for the offline (pre-computed feature) SpecAug path
  * (sp_layers.py:92-99): utt_stats[B,2,Dm] += sum_t x, sum_t x^2 over t < feat_len. */
@@ -157,8 +171,8 @@ SPL_API int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N,
 /* kernel-A engine a call with this sample format runs on: "umma" (tcgen05 DFT-as-GEMM), "fft", "simple" */
 SPL_API const char* spl_engine_name(const spl_handle* h, int32_t sample_format);
 /* Host-only (no device needed): the tcgen05 engine's tables for a configuration, for the CPU model of the kernel
- * in tests/ (tools/emulate_umma.py).  fmt 0 = fp32 samples, 1 = int16.  info[6] = {supported, twiddle bytes, table
- * floats, offset of the mel weights, offset of the shift codes, trailing emits}.  Buffers may be NULL to query sizes. */
+ * in tests/ (tools/emulate_umma.py).  fmt 0 = fp32 samples, 1 = int16.  info[11] = {supported, twiddle bytes, table
+ * floats, offset of the mel weights, offset of the shift codes, trailing emits, epilogue parts, first filter of part 0..3}.  Buffers may be NULL to query sizes. */
 SPL_API int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* window, const float* mel_dense,
                                   int32_t fmt, void* twiddles, size_t twiddle_cap, float* tab, size_t tab_cap,
                                   int32_t* info);

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libspl_b200.so")
 
-SPL_ABI_VERSION = 1
+SPL_ABI_VERSION = 2
 SPL_OK = 0
 CMVN_MODES = {"none": 0, "utterance": 1, "global": 2}
 SAMPLES_F32, SAMPLES_I16 = 0, 1
@@ -65,12 +65,15 @@ class SplPostArgs(C.Structure):
         ("n_freq_masks", C.c_int32),
         ("n_time_masks", C.c_int32),
         ("mask_params", C.c_void_p),
+        ("mask_uniforms", C.c_void_p),
+        ("freq_mask_width", C.c_float),
+        ("time_mask_width", C.c_float),
     ]
 
 
 EXPORTS = ("spl_create", "spl_destroy", "spl_fbank_forward", "spl_post_inplace", "spl_column_stats",
            "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest", "spl_specaug_rects",
-           "spl_conv0_relu", "spl_fbank_forward_multi", "spl_engine_name", "spl_debug_status", "spl_debug_umma_tables", "spl_debug_umma_acc")
+           "spl_conv0_relu", "spl_fbank_forward_multi", "spl_engine_name", "spl_debug_status", "spl_debug_umma_tables", "spl_debug_umma_acc", "spl_post_inplace_multi", "spl_forward_multi")
 
 _lib = None
 
@@ -105,6 +108,10 @@ def load() -> C.CDLL:
     lib.spl_debug_umma_tables.restype = C.c_int
     lib.spl_post_inplace.argtypes = [C.c_void_p, C.POINTER(SplPostArgs), C.c_void_p]
     lib.spl_post_inplace.restype = C.c_int
+    lib.spl_post_inplace_multi.argtypes = [C.c_void_p, C.POINTER(SplPostArgs), C.c_int32, C.c_void_p]
+    lib.spl_post_inplace_multi.restype = C.c_int
+    lib.spl_forward_multi.argtypes = [C.c_void_p, C.POINTER(SplFbankArgs), C.POINTER(SplPostArgs), C.c_int32, C.c_void_p]
+    lib.spl_forward_multi.restype = C.c_int
     lib.spl_column_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]
     lib.spl_column_stats.restype = C.c_int

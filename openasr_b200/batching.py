@@ -142,7 +142,10 @@ class PinnedWaveCollator:
         if self.device.type != "cuda":
             raise RuntimeError("PinnedWaveCollator needs a CUDA device (no CPU path)")
         self._dtype = torch.int16 if int16 else torch.float32
-        self._host = [torch.zeros((max_batch, max_len), dtype=self._dtype).pin_memory() for _ in range(slots)]
+        # flat pinned slots: every batch is padded into a CONTIGUOUS [B, L] view of its slot, so the H2D copy is a
+        # single asynchronous DMA (a strided [:B, :L] slice of a [max_batch, max_len] buffer would be staged through
+        # a pageable temporary by torch and block the host)
+        self._host = [torch.zeros((max_batch * max_len,), dtype=self._dtype).pin_memory() for _ in range(slots)]
         self._done = [None] * slots
         self._next = 0
         self._stream = torch.cuda.Stream(device=self.device)
@@ -156,10 +159,14 @@ class PinnedWaveCollator:
             waveforms = [np.asarray(w, dtype=np.float32) for w in waveforms]
         elif not all(w.dtype == np.int16 for w in waveforms):
             raise TypeError("this collator was built for int16 PCM; pass int16=False for float input")
-        host, lengths = pad_wave_batch(waveforms, out=self._host[s])
+        B, L = len(waveforms), max(int(w.shape[0]) for w in waveforms)
+        if B * L > self._host[s].numel():
+            raise ValueError("batch of %d x %d samples exceeds the collator's slot (%d)" % (B, L, self._host[s].numel()))
+        host, lengths = pad_wave_batch(waveforms, out=self._host[s][:B * L].view(B, L))
+        assert host.is_contiguous() and host.is_pinned()
         with torch.cuda.stream(self._stream):
             dev = torch.empty(host.shape, dtype=host.dtype, device=self.device)
-            dev.copy_(host, non_blocking=True)  # strided pinned source rows: one 2-D copy
+            dev.copy_(host, non_blocking=True)  # contiguous pinned source: one asynchronous copy
             ev = torch.cuda.Event()
             ev.record(self._stream)
         self._done[s] = ev

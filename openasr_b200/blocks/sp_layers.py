@@ -18,6 +18,9 @@ Optional extension keys; the defaults reproduce the reference's behaviour:
     cmvn_norm_vars : True
     dither_rng     : "device" (Philox stream on the GPU, same distribution) |
                      "host"   (the reference's exact CPU-generator stream, uploaded; parity mode)
+    sync_free      : False    (True: CUDA ``lengths`` are never read back -- T comes from the padded width, which
+                               the reference's collate makes equal to the longest utterance; the too-short
+                               utterance assertion then only covers the padded width)
     specaug_rng    : "host"   (uniforms from the CPU default generator in the reference's draw
                                order: bit-exact against the reference run on CPU) |
                      "device" (torch.rand on the feature device, as the reference does on a GPU)
@@ -51,6 +54,9 @@ class SPLayer(nn.Module):
             sa = config["spec_aug"]
             self.spec_aug_conf = {k: sa[k] for k in
                                   ("freq_mask_num", "freq_mask_width", "time_mask_num", "time_mask_width")}
+            # limits of kernel B, checked here rather than at the first call (spl_post_inplace: <= 32 masks)
+            if int(sa["freq_mask_num"]) + int(sa["time_mask_num"]) > 32 or min(int(sa["freq_mask_num"]), int(sa["time_mask_num"])) < 0:
+                raise ValueError("spec_aug: freq_mask_num + time_mask_num must be in [0, 32]")
         self.num_ceps = None
         if self.feature_type == "offline":
             self.func = None
@@ -59,6 +65,11 @@ class SPLayer(nn.Module):
             self._use_energy = bool(config["use_energy"])
             self._num_mel_bins = int(config["num_mel_bins"])
             self._shift, self._win, self._padded = tables.frame_geometry(self._sample_rate)
+            if self._padded not in (256, 512):
+                raise ValueError("sample_rate %s gives a %d-point padded window; the B200 kernels support 256 and 512 "
+                                 "(about 5.2 .. 20.4 kHz)" % (config["sample_rate"], self._padded))
+            if not 4 <= self._num_mel_bins <= 128:
+                raise ValueError("num_mel_bins must be in [4, 128]")
             self.func = self._fbank_single
         else:
             raise ValueError("Unknown feature type.")
@@ -69,6 +80,7 @@ class SPLayer(nn.Module):
         self._cmvn_norm_vars = bool(get("cmvn_norm_vars", True))
         self._dither_rng = str(get("dither_rng", "device"))
         self._specaug_rng = str(get("specaug_rng", "host"))
+        self._sync_free = bool(get("sync_free", False))
         if self._cmvn not in ("none", "utterance", "global"):
             raise ValueError("cmvn must be one of none|utterance|global")
         if self._window_type not in tables.WINDOW_TYPES:
@@ -155,6 +167,8 @@ class SPLayer(nn.Module):
         x = padded_features if (padded_features.is_contiguous() and padded_features.dtype == torch.float32) \
             else padded_features.float().contiguous()
         B, T, V = x.shape
+        if V > 160:
+            raise ValueError("spec_aug: feature rows wider than 160 are not supported by kernel B (got %d)" % V)
         flen_dev = torch.as_tensor(feature_lengths).long().to(x.device)
         frames = None if (isinstance(feature_lengths, torch.Tensor) and feature_lengths.is_cuda) \
             else [int(v) for v in torch.as_tensor(feature_lengths).tolist()]
@@ -180,47 +194,101 @@ class SPLayer(nn.Module):
         need_stats = self._cmvn == "utterance" or (aug and int(self.spec_aug_conf["time_mask_num"]) > 0)
         if self._dither_rng == "host" and self._dither != 0.0 or self._specaug_rng != "host":
             return self._forward_general(wav_batch, lengths, aug, need_stats)
+        return self.forward_multi([(wav_batch, lengths)])[0]
 
-        # ---- fast path: one pinned upload (lengths + mask rectangles), two kernel launches ----
-        dev = wav_batch.device
+    def forward_multi(self, batches):
+        """Several ``(wav_batch, lengths)`` pairs in ONE call of the library (``spl_forward_multi``): one persistent
+        launch of kernel A over all batches + one launch of kernel B, one pinned upload of the per-call integers.
+        Returns ``[(padded_features, feature_lengths), ...]`` like consecutive ``forward`` calls (host RNG: ONE dither
+        seed per call, then the SpecAug uniforms batch by batch in the reference's draw order).
+
+        ``lengths`` on the host (list / CPU tensor): frame counts, ``T = max m_i`` and the short-utterance assertion
+        (kaldi_signal.py:154) are evaluated here.  ``lengths`` as a CUDA int64 tensor with ``sync_free: True`` in the
+        config: nothing is read back -- ``T`` comes from the padded width (the collate pads to the longest utterance,
+        data_utils.py:126-138) and the SpecAug rectangles are resolved in kernel B from the uploaded uniforms."""
+        if self.func is None:
+            return [self.forward(w, l) for w, l in batches]
+        aug = self.training and self.spec_aug_conf is not None
+        need_stats = self._cmvn == "utterance" or (aug and int(self.spec_aug_conf["time_mask_num"]) > 0)
+        if self._dither_rng == "host" and self._dither != 0.0 or self._specaug_rng != "host":
+            return [self._forward_general(w, l, aug, need_stats) for w, l in batches]
+        if self._cmvn == "global" and self._gmean is None:
+            raise RuntimeError("cmvn='global' needs set_global_cmvn() (see openasr_b200.cmvn)")
+        dev = batches[0][0].device
         h = self._handle(dev)
-        if isinstance(lengths, torch.Tensor):
-            lens_np = lengths.detach().cpu().numpy().astype(np.int64, copy=False)  # one D2H sync if on the GPU
-        else:
-            lens_np = np.asarray(lengths, dtype=np.int64)
-        B = wav_batch.shape[0]
-        if lens_np.shape != (B,):
-            raise ValueError("lengths must have one entry per utterance")
-        n_min = int(lens_np.min())
-        assert 2 <= h.win <= n_min, "choose a window size %d that is [2, %d]" % (h.win, n_min)  # kaldi_signal.py:154
-        if int(lens_np.max()) > wav_batch.shape[1]:
-            raise ValueError("length %d exceeds the padded batch width %d" % (int(lens_np.max()), wav_batch.shape[1]))
-        frames_np = 1 + (lens_np - h.win) // h.shift
-        T = int(frames_np.max())
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self._dither != 0.0 else 0
-        arrays = [lens_np]
+        n = len(batches)
         nf = nt = 0
         if aug:
-            conf = self.spec_aug_conf
-            nf, nt = int(conf["freq_mask_num"]), int(conf["time_mask_num"])
-            u = frontend.specaug_uniforms(B, nf, nt, None).numpy()
-            arrays.append(frontend.specaug_rectangles_c(u, frames_np, T, h.d_out, conf))
+            nf, nt = int(self.spec_aug_conf["freq_mask_num"]), int(self.spec_aug_conf["time_mask_num"])
+        arrays, meta = [], []
+        seed = 0
+        for wav_batch, lengths in batches:
+            frontend._require_cuda(wav_batch, "wav_batch")
+            B = wav_batch.shape[0]
+            lens_dev = None
+            if isinstance(lengths, torch.Tensor) and lengths.is_cuda and self._sync_free:
+                if lengths.dtype != torch.int64 or lengths.shape != (B,):
+                    raise ValueError("device lengths must be an int64 tensor with one entry per utterance")
+                lens_dev = lengths.contiguous()
+                T = tables.frame_count(int(wav_batch.shape[1]), h.win, h.shift)
+                assert wav_batch.shape[1] >= h.win, "choose a window size %d that is [2, %d]" % (h.win, wav_batch.shape[1])
+            else:
+                if isinstance(lengths, torch.Tensor):
+                    lens_np = lengths.detach().cpu().numpy().astype(np.int64, copy=False)  # one D2H sync if on the GPU
+                else:
+                    lens_np = np.asarray(lengths, dtype=np.int64)
+                if lens_np.shape != (B,):
+                    raise ValueError("lengths must have one entry per utterance")
+                n_min = int(lens_np.min())
+                assert 2 <= h.win <= n_min, "choose a window size %d that is [2, %d]" % (h.win, n_min)  # kaldi_signal.py:154
+                if int(lens_np.max()) > wav_batch.shape[1]:
+                    raise ValueError("length %d exceeds the padded batch width %d" % (int(lens_np.max()), wav_batch.shape[1]))
+                T = int((1 + (lens_np - h.win) // h.shift).max())
+                arrays.append(lens_np)
+            if self._dither != 0.0 and seed == 0:
+                seed = int(torch.randint(1, 2 ** 62, (1,)).item())  # CPU generator: torch.manual_seed applies
+            uni_idx = None
+            if aug:
+                uni_idx = len(arrays)
+                arrays.append(frontend.specaug_uniforms(B, nf, nt, None).numpy())  # reference draw order, CPU generator
+            meta.append((wav_batch, lens_dev, B, T, uni_idx))
         stream = torch.cuda.current_stream(dev)  # looked up once: every launch of this call goes there
-        sptr = frontend.C.c_void_p(stream.cuda_stream)
-        keep, ptrs = self._stager.upload(arrays, dev, stream)
-        utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
-        feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)
-        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
-        h.fbank(wav_batch, ptrs[0], T, dither_seed=seed, utt_stats=utt_stats, out=feats, feat_len=feat_len,
-                stream_ptr=sptr)
-        if self._cmvn != "none" or aug:
-            if self._cmvn == "global" and self._gmean is None:
-                raise RuntimeError("cmvn='global' needs set_global_cmvn() (see openasr_b200.cmvn)")
-            frontend.post_inplace(feats, feat_len, cmvn_mode=self._cmvn, norm_vars=self._cmvn_norm_vars,
-                                  utt_stats=utt_stats, global_mean=self._gmean, global_istd=self._gistd,
-                                  mask_params=ptrs[1] if aug else None, n_freq=nf, n_time=nt, handle=h, stream_ptr=sptr)
-        del keep  # stream-ordered allocator: the block is only reused behind the launches above
-        return feats, feat_len
+        keep, ptrs = self._stager.upload(arrays, dev, stream) if arrays else (None, [])
+        fa = (frontend._capi.SplFbankArgs * n)()
+        pa = (frontend._capi.SplPostArgs * n)()
+        outs, alive = [], [keep]
+        ai = 0
+        do_post = self._cmvn != "none" or aug
+        for k, (wav_batch, lens_dev, B, T, uni_idx) in enumerate(meta):
+            if lens_dev is None:
+                lens_ptr = ptrs[ai]
+                ai += 1
+            else:
+                lens_ptr = lens_dev.data_ptr()
+            if uni_idx is not None:
+                ai += 1
+            feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)
+            feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+            utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
+            alive.append(h._fill_args(fa[k], wav_batch, lens_ptr, T, None, seed, utt_stats, None, feats, feat_len))
+            alive.append(utt_stats)
+            if do_post:
+                a = pa[k]
+                a.Dm = h.d_out
+                a.cmvn_mode = frontend._capi.CMVN_MODES[self._cmvn]
+                a.norm_vars = int(self._cmvn_norm_vars)
+                a.global_mean = self._gmean.data_ptr() if self._gmean is not None else None
+                a.global_istd = self._gistd.data_ptr() if self._gistd is not None else None
+                if aug:
+                    a.n_freq_masks, a.n_time_masks = nf, nt
+                    a.mask_uniforms = ptrs[uni_idx]
+                    a.freq_mask_width = float(self.spec_aug_conf["freq_mask_width"])
+                    a.time_mask_width = float(self.spec_aug_conf["time_mask_width"])
+            outs.append((feats, feat_len))
+        frontend._capi.check(h._lib.spl_forward_multi(h._h, fa, pa if do_post else None, n,
+                                                       frontend.C.c_void_p(stream.cuda_stream)), "spl_forward_multi")
+        del alive  # stream-ordered allocator: the blocks are only reused behind the launches above
+        return outs
 
     def _forward_general(self, wav_batch, lengths, aug, need_stats):
         """Parity-mode / device-RNG variants (host dither stream upload, torch.rand on the GPU)."""

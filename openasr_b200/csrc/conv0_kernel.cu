@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kConvThreads) conv0_relu_kernel(const float* _
     const float r[4] = {c2_re(a01), c2_im(a01), c2_re(a23), c2_im(a23)};
 #pragma unroll
     for (int k = 0; k < kConvPos; ++k)
-      if (p0 + 32 * k < plane) oc[p0 + 32 * k] = fmaxf(r[k], 0.f);
+      if (p0 + 32 * k < plane) oc[p0 + 32 * k] = r[k] > 0.f ? r[k] : (r[k] != r[k] ? r[k] : 0.f);  // torch.relu propagates NaN
   }
 }
 

@@ -62,7 +62,9 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint32_t k0, uint32_t k
 __device__ __forceinline__ float dither_term(uint32_t v24, float d2) {
   const float v = (float)max(v24, 2u);
   // -2 ln(v 2^-24) = (24 - lg2 v) * 2 ln 2
-  const float a = fmaf(fast_log2(v), -1.3862943611198906f * d2, 33.27106466687737f * d2);
+  // the two products are rounded separately: for dither values that are not powers of two `a` can come out
+  // slightly negative at lg2 v == 24 (v >= 2^24 - 11) -> clamp, sqrt.approx of a negative is NaN
+  const float a = fmaxf(fmaf(fast_log2(v), -1.3862943611198906f * d2, 33.27106466687737f * d2), 0.f);
   float cs;
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(v * 3.7450703370559213e-07f));  // 2 pi 2^-24
   return fast_sqrt(a) * cs;
@@ -223,7 +225,8 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
             float csA, csB;
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csA) : "f"(c2_re(ang)));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csB) : "f"(c2_im(ang)));
-            const c2 g = c2_mul(c2_make(fast_sqrt(c2_re(a)), fast_sqrt(c2_im(a))), c2_make(csA, csB));
+            // clamp: the separately rounded products can leave a few ulps below zero at lg2 u == 24
+            const c2 g = c2_mul(c2_make(fast_sqrt(fmaxf(c2_re(a), 0.f)), fast_sqrt(fmaxf(c2_im(a), 0.f))), c2_make(csA, csB));
             if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = c2_fma(g, c2_splat(sgn), x[n1]);  // sign of `dither`
           }
         }

@@ -26,10 +26,14 @@
 //     accumulators) -> streaming triangular mel bank (two running filters, weights from the reference's dense
 //     bank) -> log -> 16-column pieces through shared memory -> coalesced stores + fp64 column sums.
 //
-// Roles (one CTA of 23 warps per SM): warps 0-15 produce the A operand (warp w owns rows 8w..8w+7 of the
-// 128-row tile, lane = (row, octet of 8 samples)); warp 16 issues the MMAs; warp 17 streams the pre-swizzled
-// twiddle images (TMA bulk copies, 3-deep ring); warp 18 builds the tile (row table, sample staging by TMA);
-// warps 19-22 run the epilogue of tile i while the producers work on tile i+1.
+// Roles (one CTA of 19 warps per SM): warps 0-15 are the workers -- they produce the A operand of a tile (warp w
+// owns rows 8w..8w+7, lane = (row, octet of 8 samples)) and then run its epilogue together: warp w reads TMEM lane
+// quarter w % 4 and takes part w / 4 of the bins (the two filters a part boundary cuts are handed to the part
+// below through a small side buffer); the accumulators are single-buffered (4 x HALF = all 512 TMEM columns), so
+// an epilogue on few warps would serialise with the MMAs -- measured 47 k of 65 k cycles per tile with four
+// dedicated epilogue warps (profiles/r2_summary.md).  Warp 16 issues the MMAs; warp 17 streams the pre-swizzled
+// twiddle images (TMA bulk copies, 3-deep ring); warp 18 builds the next tile (row table, sample staging by TMA)
+// while the workers are in the epilogue.
 #include <cuda_fp16.h>
 
 #include "fbank_frame.cuh"
@@ -37,11 +41,22 @@
 
 namespace spl {
 
+#ifdef SPL_TRACE  // per-warp clock64 timeline of CTA 0 (tools/trace_umma.py); never defined in the shipped library
+__device__ unsigned long long g_utrace[23 * 512];
+#define UTR(tag)                                                                                                  \
+  do {                                                                                                            \
+    if (blockIdx.x == 0 && lane == 0 && tr_n < 510)                                                               \
+      g_utrace[w * 512 + tr_n++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)clock64() & 0xffffffffffffULL); \
+  } while (0)
+#else
+#define UTR(tag) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kURows = 128;
 constexpr int kUProd = 16;                  // producer warps
-constexpr int kUWarps = kUProd + 3 + 4;     // + MMA, twiddle TMA, tile setup, 4 epilogue warps
+constexpr int kUWarps = kUProd + 3;         // + MMA issuer, twiddle TMA, tile setup
 constexpr int kUThreads = kUWarps * 32;
 constexpr int kBStages = 3;                 // twiddle half-stages in flight
 constexpr int kMaxSeg = 16;                 // utterance segments per tile (more: the tile is cut short)
@@ -54,7 +69,7 @@ struct ULayout {
   int a_stage;     // 8 sub-tiles: ce_hi ce_lo co_hi co_lo se_hi se_lo so_hi so_lo
   int b_tile;      // one twiddle tile: HALF rows x 32 B
   int b_stage;     // half-stage: 4 tiles
-  int off_a, off_b, off_samp, samp_bytes, off_tab, off_stg, off_rt, off_seg, off_fpre, off_gst, off_bar, total;
+  int off_a, off_b, off_samp, samp_bytes, off_tab, off_sb, off_rt, off_seg, off_fpre, off_gst, off_bar, total;
 };
 
 // row table of one tile (double buffered)
@@ -81,13 +96,13 @@ __host__ __device__ inline ULayout make_ulayout(int nfft, int es, int tab_bytes,
   // staging: a full tile of one utterance ((127 S + Nw) samples at 16 kHz / fp32 = 82 880 B) + alignment heads
   L.samp_bytes = es == 4 ? 86016 : 45056;
   L.off_tab = L.off_samp + L.samp_bytes;
-  L.off_stg = (L.off_tab + tab_bytes + 15) & ~15;
-  L.off_rt = (L.off_stg + 4 * 32 * 17 * 4 + 15) & ~15;
+  L.off_sb = (L.off_tab + tab_bytes + 15) & ~15;   // boundary partials [3][128 rows][2]
+  L.off_rt = L.off_sb + 3 * kURows * 2 * 4;
   L.off_seg = L.off_rt + 2 * (int)sizeof(RowTab);
   L.off_fpre = L.off_seg + kMaxSeg * 16;
   L.off_gst = (L.off_fpre + (kMaxUmmaUtts + 1) * 4 + 7) & ~7;
   L.off_bar = L.off_gst + 2 * D_out * 8;
-  L.total = L.off_bar + 32 * 8;
+  L.total = L.off_bar + 40 * 8;
   return L;
 }
 
@@ -98,12 +113,13 @@ enum : int {
   BAR_AEMPTY = 3,    // [2] MMA commit -> producers
   BAR_BFULL = 5,     // [3] twiddle TMA tx -> MMA
   BAR_BEMPTY = 8,    // [3] MMA commit -> twiddle TMA
-  BAR_TFULL = 11,    // accumulators complete (commit) -> epilogue
-  BAR_TEMPTY = 12,   // epilogue drained TMEM (4 arrivals) -> MMA
+  BAR_TFULL = 11,    // accumulators complete (commit) -> workers (epilogue)
+  BAR_TEMPTY = 12,   // workers drained TMEM (16 arrivals) -> MMA
   BAR_SFULL = 13,    // samples landed (TMA tx) -> producers
   BAR_SEMPTY = 14,   // producers done with the staging buffer (16 arrivals) -> setup warp
   BAR_READY = 15,    // [2] tile published (1 arrival) -> everyone
-  BAR_COUNT = 17
+  BAR_SB = 17,       // [3 boundaries x 4 quarters] boundary partials written (1 arrival) -> the part below
+  BAR_COUNT = 29
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -118,10 +134,10 @@ __device__ __forceinline__ bool mbar_wait_or_abort(uint64_t* bar, uint32_t parit
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(2000u)  // suspend-time hint (ns): a waiting warp sleeps instead of polling
         : "memory");
     if (done) return true;
     if ((it & 63u) == 63u) {
@@ -217,8 +233,14 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
   constexpr int NSHIFT = 16 / ES;            // 4 (fp32) or 8 (int16)
   constexpr int KX = (3 * NSHIFT + 2 + 15) / 16;  // K steps of the correction chunk
   constexpr int HS_PER_TILE = 2 * (NCH + 1);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // the dynamic shared memory window starts 1024-byte aligned; pointers derived from `sm` stay in the shared
+  // state space (LDS / STS with 32-bit addresses -- an integer round-up of the base would turn every access
+  // into a generic LD / ST with 64-bit address arithmetic)
+  extern __shared__ __align__(1024) uint8_t sm[];
+  if ((smem_u32(sm) & 255u) != 0u) {  // SWIZZLE_32B tiles need 256-byte alignment
+    if (threadIdx.x == 0 && p.status) atomicCAS(p.status, 0, 0x20000);
+    return;
+  }
   const ULayout L = make_ulayout(NFFT, ES, p.tab_bytes, p.D_out);
   ST* samp = reinterpret_cast<ST*>(sm + L.off_samp);
   const float* tab = reinterpret_cast<const float*>(sm + L.off_tab);
@@ -236,6 +258,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int S = p.S, Nw = p.Nw, D_out = p.D_out, U = p.total_utts;
+  [[maybe_unused]] int tr_n = 0;
+  UTR(0);
 
   // ---- 0. barriers, TMEM, tables, frame prefix ------------------------------------------------------
   if (tid == 0) {
@@ -250,7 +274,8 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
       mbar_init(bars + BAR_BEMPTY + i, 1);
     }
     mbar_init(bars + BAR_TFULL, 1);
-    mbar_init(bars + BAR_TEMPTY, 4);
+    mbar_init(bars + BAR_TEMPTY, kUProd);
+    for (int i = 0; i < 12; ++i) mbar_init(bars + BAR_SB + i, 1);
     mbar_init(bars + BAR_SFULL, 1);
     mbar_init(bars + BAR_SEMPTY, kUProd);
     *abort_flag = 0;
@@ -352,7 +377,9 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         RowTab& rt = rtab[slot];
         const int nrows = rt.nrows;
         if (nrows == 0) break;
+        UTR(1);
         if (!mbar_wait_or_abort(bars + BAR_SFULL, tile & 1, abort_flag, BAR_SFULL | (w << 8))) goto done;  // the tile's samples have landed
+        UTR(2);
         const bool rvalid = row < nrows;
         // rows past the tile's end mirror the warp's first row (finite data, results never stored)
         const int rsrc = rvalid ? row : (8 * w < nrows ? 8 * w : 0);
@@ -398,6 +425,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
           sc = __int_as_float((127 + e) << 23);
           if (q == 0 && rvalid) rt.inv2[row] = __int_as_float((127 - 2 * e) << 23);
         }
+        UTR(3);
         const float so = -piv * sc;
         float rowsum = 0.f, zhalf = 0.f;
         float carry_j = 0.f, carry_m = 0.f;   // previous chunk's last x~ (lane q = 3) / lowest mirrored x~
@@ -438,6 +466,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
           const int st = chunk_seq & 1;
           uint8_t* stage = sm + L.off_a + st * L.a_stage;
           if (chunk_seq >= 2 && !mbar_wait_or_abort(bars + BAR_AEMPTY + st, ((chunk_seq >> 1) - 1) & 1, abort_flag, BAR_AEMPTY | (w << 8))) goto done;
+          UTR(10 + c);
           // byte offset of this lane's 8-byte slice (K columns 4q..4q+3) inside a sub-tile (SWIZZLE_32B)
           const uint32_t aoff = (uint32_t)(row * 32 + ((((q >> 1) ^ (row >> 2)) & 1) << 4) + ((q & 1) << 3));
           if (c < NCH) {
@@ -555,11 +584,208 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
           }
           fence_proxy_async();  // generic-proxy writes of the A tiles -> visible to the tensor core
           __syncwarp();
+          UTR(20 + c);
           if (lane == 0) {
             mbar_arrive(bars + BAR_AFULL + st);
             if (c == NCH - 1) mbar_arrive(bars + BAR_SEMPTY);  // every lane's last read of the staging buffer is done
           }
         }
+
+        // ---- epilogue of this tile, all workers: warp = (TMEM lane quarter eq, bin part pt) --------------------
+        if (!mbar_wait_or_abort(bars + BAR_TFULL, tile & 1, abort_flag, BAR_TFULL | (w << 8))) goto done;
+        tc::fence_after_sync();
+        UTR(111);
+        {
+          const int eq = w & 3, pt = w >> 2;
+          const int erow = 32 * eq + lane;
+          if (pt < p.nparts) {
+            const float inv2 = erow < nrows ? rt.inv2[erow] : 1.f;
+            const int my_ut = rt.ut[erow];
+            // all 32 rows of this warp valid and of one utterance (the common case): column sums without per-row checks
+            const int ut0 = __shfl_sync(0xffffffffu, my_ut, 0);
+            const bool one_utt = __all_sync(0xffffffffu, my_ut >= 0 && ((my_ut ^ ut0) & 0xffffff) == 0);
+            const bool want_utt = p.want_utt_stats != 0, want_g = p.global_stats != nullptr;
+            // staging [32 rows][17]: this warp's own 256-byte slices of the (idle) A ring -- rows 8w..8w+7 of the 16
+            // sub-tiles, which no other warp writes and the tensor core only reads after this warp's next arrival
+            uint8_t* const stg_base = sm + L.off_a + (w << 8);
+            auto stg = [&](int i) -> float& { return *reinterpret_cast<float*>(stg_base + ((i >> 6) << 12) + ((i & 63) << 2)); };
+            float* const sbuf = reinterpret_cast<float*>(sm + L.off_sb);
+            const int steps_per_part = 2 * HALF / p.nparts;
+            const int s_beg = pt * steps_per_part, s_end = s_beg + steps_per_part;
+            int outc = pt == 0 ? 0 : p.part_f0[pt] + 2;  // next output column this part finalises
+            int pc0 = outc;                              // first column of the piece being staged
+            int emitted = 0;
+            float accA = 0.f, accB = 0.f;
+            // store + column sums of the staged piece [c0, c0 + n), n <= 16
+            auto flush_piece = [&](int c0, int n) {
+              __syncwarp();
+              const int c = lane & 15, hf = lane >> 4;
+#pragma unroll 4
+              for (int it = 0; it < 16; ++it) {
+                const int r = 2 * it + hf;
+                float* o = rt.out[32 * eq + r];
+                if (c < n && o != nullptr) o[c0 + c] = stg(r * 17 + c);
+              }
+              if ((want_utt || want_g) && c < n) {
+                double s1 = 0.0, s2 = 0.0, g1 = 0.0, g2 = 0.0;
+                int cu = -1;
+                auto push = [&]() {
+                  if (cu >= 0 && want_utt) {
+                    const UBatch& bd = p.bd[batch_of(p, cu)];
+                    if (bd.utt_stats) {
+                      atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + c0 + c, s1);
+                      atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + c0 + c, s2);
+                    }
+                  }
+                  g1 += s1;
+                  g2 += s2;
+                  s1 = s2 = 0.0;
+                };
+                if (one_utt) {
+                  cu = ut0 & 0xffffff;
+                  double t1 = 0.0, t2 = 0.0;  // two independent chains
+#pragma unroll
+                  for (int i = 0; i < 16; i += 2) {
+                    const double v0 = (double)stg((16 * hf + i) * 17 + c), v1 = (double)stg((16 * hf + i + 1) * 17 + c);
+                    s1 += v0;
+                    t1 += v1;
+                    s2 = fma(v0, v0, s2);
+                    t2 = fma(v1, v1, t2);
+                  }
+                  s1 += t1;
+                  s2 += t2;
+                } else {
+                  for (int i = 0; i < 16; ++i) {
+                    const int r = 16 * hf + i;
+                    const int ut = rt.ut[32 * eq + r];
+                    const int u = ut < 0 ? -1 : (ut & 0xffffff);
+                    if (u != cu) {
+                      push();
+                      cu = u;
+                    }
+                    if (u >= 0) {
+                      const double v = (double)stg(r * 17 + c);
+                      s1 += v;
+                      s2 = fma(v, v, s2);
+                    }
+                  }
+                }
+                push();
+                if (want_g) {
+                  atomicAdd(gst + c0 + c, g1);
+                  atomicAdd(gst + D_out + c0 + c, g2);
+                }
+              }
+              __syncwarp();
+            };
+            auto finalise = [&](float e) {
+              stg(lane * 17 + (outc - pc0)) = fast_log(fmaxf(e * inv2, kEps));  // kaldi_signal.py:540
+              ++outc;
+              if (outc - pc0 == 16) {
+                flush_piece(pc0, 16);
+                pc0 = outc;
+              }
+            };
+            // A filter is complete: parts above the first hand their first two (cut by the part boundary) to the
+            // part below as raw partial sums; everything else is finalised here
+            auto emit = [&]() {
+              if (pt > 0 && emitted < 2) {
+                sbuf[((pt - 1) * kURows + erow) * 2 + emitted] = accA;
+                if (emitted == 1) {
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bars + BAR_SB + (pt - 1) * 4 + eq);
+                }
+              } else {
+                finalise(accA);
+              }
+              ++emitted;
+              accA = accB;
+              accB = 0.f;
+            };
+            const uint32_t tbase = tmem + ((uint32_t)(32 * eq) << 16);
+            if (p.debug_acc != nullptr && blockIdx.x == 0 && tile == 0 && pt == 0) {  // diagnostic: raw accumulators + 1/s^2
+              for (int c8 = 0; c8 < 4 * HALF; c8 += 8) {
+                float v[8];
+                tmem_ld8(tbase + c8, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p.debug_acc[(size_t)erow * (4 * HALF + 1) + c8 + i] = v[i];
+              }
+              p.debug_acc[(size_t)erow * (4 * HALF + 1) + 4 * HALF] = inv2;
+            }
+#pragma unroll 1
+            for (int step0 = s_beg; step0 < s_end; step0 += 8) {
+              // pass 1 (step < HALF): bin = step + 1 = column + 1;  pass 2: bin = HALF + i, column = HALF - 1 - i
+              const bool second = step0 >= HALF;
+              const int c0 = second ? (2 * HALF - 8 - step0) : step0;  // first TMEM column of the 8 read here
+              float ce[8], co[8], se[8], so2[8];
+              tmem_ld8(tbase + c0, ce);
+              tmem_ld8(tbase + HALF + c0, co);
+              tmem_ld8(tbase + 2 * HALF + c0, se);
+              tmem_ld8(tbase + 3 * HALF + c0, so2);
+              // mel weights of the eight steps (broadcast loads, issued while the TMEM loads are in flight)
+              float2 wv[8];
+              {
+                const float4* m4 = reinterpret_cast<const float4*>(melw + step0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 t4 = m4[i];
+                  wv[2 * i] = make_float2(t4.x, t4.y);
+                  wv[2 * i + 1] = make_float2(t4.z, t4.w);
+                }
+              }
+              const uint32_t ctl = (melc[step0 >> 4] >> ((step0 & 8) << 1)) & 0xffffu;
+              tmem_ld_wait();
+              float pw[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ci = second ? 7 - i : i;  // column inside the 8 (descending in pass 2)
+                const float re = second ? ce[ci] - co[ci] : ce[ci] + co[ci];
+                const float im = second ? so2[ci] - se[ci] : se[ci] + so2[ci];
+                pw[i] = fmaf(re, re, im * im);
+              }
+              if (ctl == 0u) {  // no filter ends inside these eight bins
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  accA = fmaf(wv[i].x, pw[i], accA);
+                  accB = fmaf(wv[i].y, pw[i], accB);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  uint32_t ns = (ctl >> (2 * i)) & 3u;
+                  while (ns) {  // uniform
+                    emit();
+                    --ns;
+                  }
+                  accA = fmaf(wv[i].x, pw[i], accA);
+                  accB = fmaf(wv[i].y, pw[i], accB);
+                }
+              }
+            }
+            // this warp's share of the accumulators is drained: the next tile's MMAs may overwrite them
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_TEMPTY);
+            UTR(130);
+            if (pt + 1 < p.nparts) {
+              // the two filters cut by the upper boundary: this part's tail + the head sums of the part above
+              if (!mbar_wait_or_abort(bars + BAR_SB + pt * 4 + eq, tile & 1, abort_flag, BAR_SB | (w << 8))) goto done;
+              const float v0 = accA + sbuf[(pt * kURows + erow) * 2 + 0], v1 = accB + sbuf[(pt * kURows + erow) * 2 + 1];
+              finalise(v0);
+              finalise(v1);
+            } else {
+              for (int i = 0; i < p.nflush; ++i) emit();
+            }
+            if (outc > pc0) flush_piece(pc0, outc - pc0);
+            if (want_g && w == 0 && lane == 0) atomicAdd(gcount, nrows);
+          } else {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_TEMPTY);
+          }
+        }
+        UTR(131);
       }
     }
   } else if (w == kUProd) {
@@ -574,10 +800,12 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         if (rtab[slot].nrows == 0) break;
         if (tile > 0 && !mbar_wait_or_abort(bars + BAR_TEMPTY, (tile - 1) & 1, abort_flag, BAR_TEMPTY | (w << 8))) break;
         tc::fence_after_sync();
+        UTR(40);
         bool ok = true;
         for (int c = 0; c <= NCH && ok; ++c, ++chunk_seq) {
           const int st = chunk_seq & 1;
           if (!mbar_wait_or_abort(bars + BAR_AFULL + st, (chunk_seq >> 1) & 1, abort_flag, BAR_AFULL | (w << 8))) { ok = false; break; }
+          UTR(50 + c);
           const uint32_t a_st = a_base + st * L.a_stage;
           const bool mirror = c < NCH && (NFFT - 32 * c - 32 < Nw + NSHIFT - 1);
           for (int hf = 0; hf < 2; ++hf, ++hs_seq) {
@@ -609,6 +837,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
           }
           if (!ok) break;
           tc::commit(bars + BAR_AEMPTY + st);
+          UTR(70 + c);
         }
         if (!ok) break;
         tc::commit(bars + BAR_TFULL);
@@ -627,6 +856,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         for (int i = 0; i < HS_PER_TILE; ++i, ++hs_seq) {
           const int bs = hs_seq % kBStages;
           if (hs_seq >= kBStages && !mbar_wait_or_abort(bars + BAR_BEMPTY + bs, (hs_seq / kBStages - 1) & 1, abort_flag, BAR_BEMPTY | (w << 8))) { ok = false; break; }
+          UTR(90);
           mbar_expect_tx(bars + BAR_BFULL + bs, (uint32_t)L.b_stage);
           bulk_g2s(sm + L.off_b + bs * L.b_stage, p.twiddles + (size_t)i * L.b_stage, (uint32_t)L.b_stage, bars + BAR_BFULL + bs);
         }
@@ -686,8 +916,10 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         nseg = __shfl_sync(0xffffffffu, nseg, 0);
         u_hint = __shfl_sync(0xffffffffu, u_hint, 0);
       }
+      UTR(100);
       if (tile > 0 && !mbar_wait_or_abort(bars + BAR_SEMPTY, (tile - 1) & 1, abort_flag, BAR_SEMPTY | (w << 8))) break;
       __syncwarp();
+      UTR(101);
       if (nrows > 0) {
         // stage the segments: TMA bulk copy from the 16-byte floor, or warp loads when the envelope would leave the batch
         uint32_t tx = 0;
@@ -716,6 +948,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
           }
         }
         if (lane == 0) mbar_expect_tx(bars + BAR_SFULL, tx);  // tx == 0: plain arrival
+        UTR(102);
         // row table while the copies are in flight
         for (int r = lane; r < kURows; r += 32) {
           int ut = -1, off = 0, tt = 0;
@@ -745,133 +978,18 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         __threadfence_block();
         mbar_arrive(bars + BAR_READY + slot);
       }
+      UTR(103);
       __syncwarp();
       if (nrows == 0) break;
       pos += nrows;
     }
-  } else {
-    // ---- epilogue: thread per frame --------------------------------------------------------------------
-    const int wq = w & 3;                       // TMEM lane quarter this warp may access
-    const int row = 32 * wq + lane;
-    float* stg = reinterpret_cast<float*>(sm + L.off_stg) + wq * 32 * 17;
-    const bool want_utt = p.want_utt_stats != 0, want_g = p.global_stats != nullptr;
-    int my_rows = 0;
-    for (int tile = 0;; ++tile) {
-      const int slot = tile & 1;
-      if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) goto done;
-      RowTab& rt = rtab[slot];
-      const int nrows = rt.nrows;
-      if (nrows == 0) break;
-      if (!mbar_wait_or_abort(bars + BAR_TFULL, tile & 1, abort_flag, BAR_TFULL | (w << 8))) goto done;
-      tc::fence_after_sync();
-      const float inv2 = row < nrows ? rt.inv2[row] : 1.f;
-      if (wq == 0 && lane == 0) my_rows += nrows;
-      float accA = 0.f, accB = 0.f;
-      int col = 0;
-      // store + column sums of the 16-column piece [c0, c0 + n) staged by this warp
-      auto flush_piece = [&](int c0, int n) {
-        __syncwarp();
-        const int c = lane & 15, hf = lane >> 4;
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int r = 2 * it + hf;
-          float* o = rt.out[32 * wq + r];
-          if (c < n && o != nullptr) o[c0 + c] = stg[r * 17 + c];
-        }
-        if ((want_utt || want_g) && c < n) {
-          double s1 = 0.0, s2 = 0.0, g1 = 0.0, g2 = 0.0;
-          int cu = -1;
-          auto push = [&]() {
-            if (cu >= 0 && want_utt) {
-              const UBatch& bd = p.bd[batch_of(p, cu)];
-              if (bd.utt_stats) {
-                atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + c0 + c, s1);
-                atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + c0 + c, s2);
-              }
-            }
-            g1 += s1;
-            g2 += s2;
-            s1 = s2 = 0.0;
-          };
-          for (int i = 0; i < 16; ++i) {
-            const int r = 16 * hf + i;
-            const int ut = rt.ut[32 * wq + r];
-            const int u = ut < 0 ? -1 : (ut & 0xffffff);
-            if (u != cu) {
-              push();
-              cu = u;
-            }
-            if (u >= 0) {
-              const double v = (double)stg[r * 17 + c];
-              s1 += v;
-              s2 = fma(v, v, s2);
-            }
-          }
-          push();
-          if (want_g) {
-            atomicAdd(gst + c0 + c, g1);
-            atomicAdd(gst + D_out + c0 + c, g2);
-          }
-        }
-        __syncwarp();
-      };
-      auto emit = [&]() {
-        stg[lane * 17 + (col & 15)] = fast_log(fmaxf(accA * inv2, kEps));  // kaldi_signal.py:540
-        accA = accB;
-        accB = 0.f;
-        ++col;
-        if ((col & 15) == 0) flush_piece(col - 16, 16);
-      };
-      const uint32_t tbase = tmem + ((uint32_t)(32 * wq) << 16);
-      if (p.debug_acc != nullptr && blockIdx.x == 0 && tile == 0) {  // diagnostic: raw accumulators [row][4 HALF] + 1/s^2
-        for (int c8 = 0; c8 < 4 * HALF; c8 += 8) {
-          float v[8];
-          tmem_ld8(tbase + c8, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p.debug_acc[(size_t)row * (4 * HALF + 1) + c8 + i] = v[i];
-        }
-        p.debug_acc[(size_t)row * (4 * HALF + 1) + 4 * HALF] = inv2;
-      }
-#pragma unroll 1
-      for (int step0 = 0; step0 < 2 * HALF; step0 += 8) {
-        // pass 1 (step < HALF): bin = step + 1 = column + 1;  pass 2: bin = HALF + i, column = HALF - 1 - i
-        const bool second = step0 >= HALF;
-        const int c0 = second ? (2 * HALF - 8 - step0) : step0;  // first TMEM column of the 8 read here
-        float ce[8], co[8], se[8], so2[8];
-        tmem_ld8(tbase + c0, ce);
-        tmem_ld8(tbase + HALF + c0, co);
-        tmem_ld8(tbase + 2 * HALF + c0, se);
-        tmem_ld8(tbase + 3 * HALF + c0, so2);
-        tmem_ld_wait();
-        const uint32_t ctl = (melc[step0 >> 4] >> ((step0 & 8) << 1)) & 0xffffu;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ci = second ? 7 - i : i;  // column inside the 8 (descending in pass 2)
-          const float re = second ? ce[ci] - co[ci] : ce[ci] + co[ci];
-          const float im = second ? so2[ci] - se[ci] : se[ci] + so2[ci];
-          const float pw = fmaf(re, re, im * im);
-          uint32_t ns = (ctl >> (2 * i)) & 3u;
-          while (ns) {  // uniform
-            emit();
-            --ns;
-          }
-          const float2 wv = melw[step0 + i];
-          accA = fmaf(wv.x, pw, accA);
-          accB = fmaf(wv.y, pw, accB);
-        }
-      }
-      // the accumulators of this tile are drained: the next tile's MMAs may overwrite them
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BAR_TEMPTY);
-      for (int i = 0; i < p.nflush; ++i) emit();
-      if (col & 15) flush_piece(col & ~15, col & 15);
-    }
-    if (want_g && wq == 0 && lane == 0) atomicAdd(gcount, my_rows);
   }
 
 done:
+  UTR(200);
+#ifdef SPL_TRACE
+  if (blockIdx.x == 0 && lane == 0) g_utrace[w * 512 + 511] = (unsigned long long)tr_n;
+#endif
   tc::fence_before_sync();
   __syncthreads();
   if (p.global_stats != nullptr && !*abort_flag) {
@@ -882,6 +1000,12 @@ done:
   if (*abort_flag && tid == 0 && p.status) atomicCAS(p.status, 0, *abort_flag);
   if (w == kUProd) tc::tmem_dealloc<TMEM_COLS>(tmem);
 }
+
+#ifdef SPL_TRACE
+extern "C" __attribute__((visibility("default"))) int spl_debug_utrace(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_utrace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 template <int NFFT, typename ST, int NOISE>

@@ -23,23 +23,56 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
   __shared__ __align__(16) float s_istd[kMaxDm];
   __shared__ __align__(16) float s_tm[kMaxDm];
   __shared__ int s_mask[2 * kMaxMasks];
-  const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
+  // blockIdx.y = flattened utterance over the batches of the call
+  int kb = 0;
+#pragma unroll 1
+  for (int i = 1; i < p.nb; ++i)
+    if ((int)blockIdx.y >= p.bd[i].u0) kb = i;
+  const PostBatch& bd = p.bd[kb];
+  const int b = blockIdx.y - bd.u0, t0 = blockIdx.x * kPostRows;
+  const int T = bd.T;
+  if (t0 >= T) return;
+  float* const feats = bd.feats;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Dm = p.Dm;
-  const int nmask = p.mask_params ? (p.n_freq + p.n_time) : 0;
+  const bool have_masks = bd.mask_params != nullptr || bd.mask_uniforms != nullptr;
+  const int nmask = have_masks ? (p.n_freq + p.n_time) : 0;
   // every global load of the prologue is issued before the first use (one L2 round trip, not three)
-  const long long len64 = p.feat_len[b];
+  const long long len64 = bd.feat_len[b];
   double s1 = 0.0, s2 = 0.0;
-  if (p.utt_stats && tid < Dm) {
-    s1 = p.utt_stats[((size_t)b * 2 + 0) * Dm + tid];
-    s2 = p.utt_stats[((size_t)b * 2 + 1) * Dm + tid];
+  if (bd.utt_stats && tid < Dm) {
+    s1 = bd.utt_stats[((size_t)b * 2 + 0) * Dm + tid];
+    s2 = bd.utt_stats[((size_t)b * 2 + 1) * Dm + tid];
   }
   int my_mask = 0;
-  if (tid < 2 * nmask) my_mask = p.mask_params[(size_t)b * 2 * nmask + tid];
+  float uw = 0.f, us = 0.f;
+  if (bd.mask_params) {
+    if (tid < 2 * nmask) my_mask = bd.mask_params[(size_t)b * 2 * nmask + tid];
+  } else if (tid < nmask) {  // uniforms in the reference's draw order: row 2j = width draw, row 2j+1 = start draw
+    uw = bd.mask_uniforms[(size_t)(2 * tid) * bd.B + b];
+    us = bd.mask_uniforms[(size_t)(2 * tid + 1) * bd.B + b];
+  }
   const int len = (int)len64;
 
   // rows this CTA has to touch: valid rows, plus padding rows hit by a (spilled) time mask
-  if (tid < 2 * nmask) s_mask[tid] = my_mask;
+  if (bd.mask_params) {
+    if (tid < 2 * nmask) s_mask[tid] = my_mask;
+  } else if (tid < nmask) {
+    // sp_layers.py:59-62 / :68-71 in the reference's float32 arithmetic ((W * rand).long(),
+    // ((limit - width).float() * rand).long()), then the Python slice semantics of x[b, s:s+w] (:64, :73);
+    // same code as the host helper spl_specaug_rects
+    const bool is_f = tid < p.n_freq;
+    const long long size = is_f ? Dm : T;
+    const long long width = (long long)__fmul_rn(is_f ? p.freq_width : p.time_width, uw);
+    const long long limit = is_f ? (long long)Dm : len64;
+    const long long start = (long long)__fmul_rn(__ll2float_rn(limit - width), us);
+    const long long end = start + width;
+    long long s_ = start < 0 ? start + size : start, e_ = end < 0 ? end + size : end;
+    s_ = s_ < 0 ? 0 : (s_ > size ? size : s_);
+    e_ = e_ < 0 ? 0 : (e_ > size ? size : e_);
+    s_mask[2 * tid] = (int)s_;
+    s_mask[2 * tid + 1] = (int)(e_ > s_ ? e_ : s_);
+  }
   __syncthreads();
   int t_hi = len;
   for (int j = p.n_freq; j < nmask; ++j) {
@@ -68,7 +101,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
   }
   __syncthreads();
 
-  const int tend = min(min(t0 + kPostRows, p.T), t_hi);
+  const int tend = min(min(t0 + kPostRows, T), t_hi);
   const float inv_d = 1.0f / (float)Dm;
   const bool need_fm = p.n_freq > 0 && nmask > 0;
   constexpr int kWarpsB = kPostThreads / 32;
@@ -86,7 +119,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
         for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
         tm[r] = tmask && t < tend;
         live[r] = t < tend && !tmask && t < len;  // padding stays exactly 0 (freq means of a zero row are 0)
-        const float4* row4 = reinterpret_cast<const float4*>(p.feats + ((size_t)b * p.T + t) * Dm);
+        const float4* row4 = reinterpret_cast<const float4*>(feats + ((size_t)b * T + t) * Dm);
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
           const int g = lane + 32 * i;
@@ -118,7 +151,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int t = tb + r * kWarpsB;
-        float4* row4 = reinterpret_cast<float4*>(p.feats + ((size_t)b * p.T + t) * Dm);
+        float4* row4 = reinterpret_cast<float4*>(feats + ((size_t)b * T + t) * Dm);
         if (tm[r]) {  // may legitimately touch padding rows (reference quirk for len < width)
           for (int g = lane; g < q; g += 32) row4[g] = reinterpret_cast<const float4*>(s_tm)[g];
           continue;
@@ -144,7 +177,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
       for (int r = 0; r < RB; ++r) {
         const int t = tb + r * kWarpsB;
         if (t >= tend) break;
-        float* row = p.feats + ((size_t)b * p.T + t) * Dm;
+        float* row = feats + ((size_t)b * T + t) * Dm;
         bool tmask = false;
         for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
         if (tmask) {
@@ -185,8 +218,15 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
 }
 
 cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
-  dim3 grid((p.T + kPostRows - 1) / kPostRows, p.B);
-  const bool vec = (p.Dm & 3) == 0 && p.Dm <= 256 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
+  int tmax = 1, utts = 0;
+  bool aligned = true;
+  for (int k = 0; k < p.nb; ++k) {
+    tmax = p.bd[k].T > tmax ? p.bd[k].T : tmax;
+    utts += p.bd[k].B;
+    aligned = aligned && (reinterpret_cast<uintptr_t>(p.bd[k].feats) & 15) == 0;
+  }
+  dim3 grid((tmax + kPostRows - 1) / kPostRows, utts);
+  const bool vec = (p.Dm & 3) == 0 && p.Dm <= 256 && aligned;
   if (vec && p.Dm <= 128)
     post_kernel<true, 1><<<grid, kPostThreads, 0, st>>>(p);
   else if (vec)

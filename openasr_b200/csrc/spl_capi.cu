@@ -62,7 +62,7 @@ struct spl_handle {
   bool umma_ok[2];
   const uint8_t* umma_tw[2];
   const float* umma_tab[2];
-  int umma_tab_bytes[2], umma_off_melw[2], umma_off_melc[2], umma_nflush;
+  int umma_tab_bytes[2], umma_off_melw[2], umma_off_melc[2], umma_nflush, umma_nparts, umma_part_f0[4];
   int umma_ctas;     // grid of the tcgen05 engine (SM count; SPL_UMMA_CTAS overrides, diagnostics)
 };
 
@@ -249,6 +249,8 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.wt_off_tw = (int32_t)wt_tw;
   h->tab.nj = nj;
   h->umma_nflush = ut.nflush;
+  h->umma_nparts = ut.nparts;
+  for (int i = 0; i < 4; ++i) h->umma_part_f0[i] = ut.part_f0[i];
   for (int f = 0; f < 2; ++f) {
     h->umma_ok[f] = ut.ok && !ut.tab[f].empty();
     h->umma_tab[f] = fb + o_utab[f];
@@ -386,6 +388,8 @@ cudaError_t launch_umma(spl_handle* h, const spl_fbank_args* v, int n, cudaStrea
   p.seed_hi = (uint32_t)(v[0].dither_seed >> 32);
   p.nb = n;
   p.nflush = h->umma_nflush;
+  p.nparts = h->umma_nparts;
+  for (int i = 0; i < 4; ++i) p.part_f0[i] = h->umma_part_f0[i];
   p.global_stats = v[0].global_stats;
   p.status = h->status;
   p.debug_acc = h->debug_acc;
@@ -503,6 +507,8 @@ int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* wind
   info[3] = ut.off_melw[fmt];
   info[4] = ut.off_melc[fmt];
   info[5] = ut.nflush;
+  info[6] = ut.nparts;
+  for (int i = 0; i < 4; ++i) info[7 + i] = ut.part_f0[i];
   if (!info[0]) return SPL_OK;
   if (twiddles && twiddle_cap >= ut.twiddles[fmt].size()) std::memcpy(twiddles, ut.twiddles[fmt].data(), ut.twiddles[fmt].size());
   if (tab && tab_cap >= ut.tab[fmt].size()) std::memcpy(tab, ut.tab[fmt].data(), ut.tab[fmt].size() * 4);
@@ -524,42 +530,100 @@ const char* spl_engine_name(const spl_handle* h, int32_t sample_format) {
   return (h->engine == ENGINE_SIMPLE || !h->fft_ok) ? "simple" : "fft";
 }
 
-int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream) {
-  if (!a || !a->feats || !a->feat_len) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: null argument");
-  if (a->B < 1 || a->B > 65535 || a->T < 1 || a->Dm < 1 || a->Dm > spl::kMaxDm)
+namespace {
+
+int check_post_args(const spl_post_args* a, const spl_post_args* first) {
+  if (!a->feats || !a->feat_len) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: null argument");
+  if (a->B < 1 || a->B > (1 << 22) || a->T < 1 || a->Dm < 1 || a->Dm > spl::kMaxDm)
     return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: B/T/Dm out of range (Dm <= 160)");
-  const int nmask = a->mask_params ? a->n_freq_masks + a->n_time_masks : 0;
+  const bool masks = a->mask_params || a->mask_uniforms;
+  const int nmask = masks ? a->n_freq_masks + a->n_time_masks : 0;
   if (a->n_freq_masks < 0 || a->n_time_masks < 0 || nmask > spl::kMaxMasks)
     return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: at most 32 masks per utterance");
   if (a->cmvn_mode == SPL_CMVN_UTTERANCE && !a->utt_stats)
     return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: utterance CMVN needs utt_stats");
   if (a->cmvn_mode == SPL_CMVN_GLOBAL && (!a->global_mean || (a->norm_vars && !a->global_istd)))
     return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: global CMVN needs global_mean/global_istd");
-  if (a->mask_params && a->n_time_masks > 0 && !a->utt_stats)
+  if (masks && a->n_time_masks > 0 && !a->utt_stats)
     return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: time masks need utt_stats (time means)");
-  if (a->cmvn_mode == SPL_CMVN_NONE && nmask == 0) return SPL_OK;  // nothing to do
+  if (a->Dm != first->Dm || a->cmvn_mode != first->cmvn_mode || a->norm_vars != first->norm_vars ||
+      a->n_freq_masks != first->n_freq_masks || a->n_time_masks != first->n_time_masks ||
+      a->global_mean != first->global_mean || a->global_istd != first->global_istd ||
+      a->freq_mask_width != first->freq_mask_width || a->time_mask_width != first->time_mask_width ||
+      masks != (first->mask_params || first->mask_uniforms))
+    return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace_multi: the batches of one call must share Dm, CMVN and mask settings");
+  return SPL_OK;
+}
+
+}  // namespace
+
+int spl_post_inplace_multi(spl_handle* h, const spl_post_args* args, int32_t n, void* stream) {
+  if (!args || n < 1) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: null argument");
+  for (int i = 0; i < n; ++i) {
+    const int rc = check_post_args(args + i, args);
+    if (rc != SPL_OK) return rc;
+  }
+  const bool masks = args[0].mask_params || args[0].mask_uniforms;
+  if (args[0].cmvn_mode == SPL_CMVN_NONE && (!masks || args[0].n_freq_masks + args[0].n_time_masks == 0)) return SPL_OK;
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   DeviceGuard guard(h ? h->device : cur_dev);
   if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_post_inplace: cudaSetDevice failed");
-  spl::PostParams p;
-  p.feats = a->feats;
-  p.feat_len = a->feat_len;
-  p.B = a->B;
-  p.T = a->T;
-  p.Dm = a->Dm;
-  p.cmvn_mode = a->cmvn_mode;
-  p.norm_vars = a->norm_vars;
-  p.utt_stats = a->utt_stats;
-  p.global_mean = a->global_mean;
-  p.global_istd = a->global_istd;
-  p.n_freq = a->mask_params ? a->n_freq_masks : 0;
-  p.n_time = a->mask_params ? a->n_time_masks : 0;
-  p.mask_params = a->mask_params;
-  cudaError_t e = spl::launch_post(p, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return fail_cuda(e, "spl_post_inplace: launch");
-  g_launches.fetch_add(1);
+  for (int i0 = 0; i0 < n; i0 += spl::kMaxPostBatches) {
+    spl::PostParams p;
+    std::memset(&p, 0, sizeof(p));
+    const spl_post_args& a0 = args[0];
+    p.Dm = a0.Dm;
+    p.cmvn_mode = a0.cmvn_mode;
+    p.norm_vars = a0.norm_vars;
+    p.n_freq = masks ? a0.n_freq_masks : 0;
+    p.n_time = masks ? a0.n_time_masks : 0;
+    p.freq_width = a0.freq_mask_width;
+    p.time_width = a0.time_mask_width;
+    p.global_mean = a0.global_mean;
+    p.global_istd = a0.global_istd;
+    p.nb = std::min<int>(spl::kMaxPostBatches, n - i0);
+    int u0 = 0;
+    for (int k = 0; k < p.nb; ++k) {
+      const spl_post_args& a = args[i0 + k];
+      spl::PostBatch& b = p.bd[k];
+      b.feats = a.feats;
+      b.feat_len = a.feat_len;
+      b.utt_stats = a.utt_stats;
+      b.mask_params = a.mask_params;
+      b.mask_uniforms = a.mask_params ? nullptr : a.mask_uniforms;
+      b.B = a.B;
+      b.T = a.T;
+      b.u0 = u0;
+      u0 += a.B;
+    }
+    if (u0 > 65535) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: more than 65535 utterances in one launch");
+    cudaError_t e = spl::launch_post(p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "spl_post_inplace: launch");
+    g_launches.fetch_add(1);
+  }
   return SPL_OK;
+}
+
+int spl_post_inplace(spl_handle* h, const spl_post_args* a, void* stream) {
+  if (!a) return fail(SPL_ERR_INVALID_ARG, "spl_post_inplace: null argument");
+  return spl_post_inplace_multi(h, a, 1, stream);
+}
+
+int spl_forward_multi(spl_handle* h, const spl_fbank_args* fbank, const spl_post_args* post, int32_t n, void* stream) {
+  if (!h || !fbank || n < 1) return fail(SPL_ERR_INVALID_ARG, "spl_forward_multi: null argument");
+  int rc = spl_fbank_forward_multi(h, fbank, n, stream);
+  if (rc != SPL_OK || !post) return rc;
+  std::vector<spl_post_args> pa(post, post + n);
+  for (int i = 0; i < n; ++i) {
+    if (!pa[i].feats) pa[i].feats = fbank[i].feats;
+    if (!pa[i].feat_len) pa[i].feat_len = fbank[i].feat_len;
+    if (!pa[i].utt_stats) pa[i].utt_stats = fbank[i].utt_stats;
+    if (!pa[i].B) pa[i].B = fbank[i].B;
+    if (!pa[i].T) pa[i].T = fbank[i].T;
+    if (!pa[i].Dm) pa[i].Dm = h->D_out;
+  }
+  return spl_post_inplace_multi(h, pa.data(), n, stream);
 }
 
 int spl_column_stats(spl_handle* h, const float* feats, const int64_t* feat_len, int32_t B, int32_t T, int32_t Dm,

@@ -57,16 +57,25 @@ struct FbankParams {
   Tables tab;
 };
 
-struct PostParams {
+constexpr int kMaxPostBatches = 8;
+
+struct PostBatch {  // one batch of a (multi-)call of kernel B
   float* feats;
   const int64_t* feat_len;
-  int32_t B, T, Dm;
-  int32_t cmvn_mode, norm_vars;
   const double* utt_stats;
+  const int32_t* mask_params;   // [B, F+T, 2] resolved rectangles, or NULL
+  const float* mask_uniforms;   // [2 (F+T), B] uniforms in the reference's draw order (resolved in the kernel), or NULL
+  int32_t B, T;
+  int32_t u0;                   // first flattened utterance of the batch
+  int32_t pad_;
+};
+
+struct PostParams {
+  int32_t Dm, cmvn_mode, norm_vars, n_freq, n_time, nb;
+  float freq_width, time_width;
   const float* global_mean;
   const float* global_istd;
-  int32_t n_freq, n_time;
-  const int32_t* mask_params;
+  PostBatch bd[kMaxPostBatches];
 };
 
 // host-side launchers (defined in the .cu files); return cudaError_t of the launch
@@ -107,6 +116,7 @@ struct UmmaParams {
   float preemph, dither;
   uint32_t seed_lo, seed_hi;
   int32_t nb, total_utts, nflush, want_utt_stats;
+  int32_t nparts, part_f0[4];  // epilogue: bin parts (1, 2 or 4) and the filter the running sums start on in each part
   double* global_stats;
   int32_t* status;          // device word: 0x10000 | barrier | warp << 8 of the first barrier wait that timed out
   float* debug_acc;         // diagnostics: raw accumulators of tile 0 of CTA 0, [128][4 HALF + 1], or NULL
@@ -123,6 +133,7 @@ size_t fbank_umma_smem_bytes(int nfft, int es, int tab_bytes, int D_out);
 struct UmmaHostTables {
   bool ok = false;
   int nflush = 0;
+  int nparts = 1, part_f0[4] = {0, 0, 0, 0};
   int off_melw[2] = {0, 0}, off_melc[2] = {0, 0};  // float offsets inside tab[fmt]
   std::vector<uint8_t> twiddles[2];  // [0] fp32 samples (4 shifts), [1] int16 samples (8 shifts)
   std::vector<float> tab[2];

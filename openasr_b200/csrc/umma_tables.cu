@@ -88,6 +88,26 @@ void build_umma_tables(int nfft, int Nw, int D, const float* window, const float
       if (std::fabs(E[m] - ref[m]) > 1e-9 * (1.0 + std::fabs(ref[m]))) return;
   }
 
+  // epilogue parts: the steps are split evenly over 4 (or 2, or 1) warps per TMEM lane quarter; a part above the
+  // first hands its first two emitted filters to the part below, so it needs at least two emits of its own
+  out.nparts = 1;
+  for (int np = 4; np >= 2 && out.nparts == 1; np >>= 1) {
+    const int spp = nb / np;
+    bool ok = spp % 8 == 0;
+    int f = 0, f0[4] = {0, 0, 0, 0};
+    for (int pt = 0; pt < np && ok; ++pt) {
+      f0[pt] = f;
+      int emits = 0;
+      for (int s = pt * spp; s < (pt + 1) * spp; ++s) emits += (int)((melc[s >> 4] >> (2 * (s & 15))) & 3u);
+      f += emits;
+      if (pt > 0 && emits < 2) ok = false;
+    }
+    if (ok) {
+      out.nparts = np;
+      for (int pt = 0; pt < 4; ++pt) out.part_f0[pt] = f0[pt];
+    }
+  }
+
   const size_t b_tile = (size_t)half * 32, b_stage = 4 * b_tile;
   for (int fmt = 0; fmt < 2; ++fmt) {
     const int nshift = fmt == 0 ? 4 : 8;

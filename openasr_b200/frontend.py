@@ -310,44 +310,55 @@ def specaug_rectangles_c(uniforms: np.ndarray, frames: np.ndarray, T: int, V: in
 
 
 class HostStager:
-    """Ring of pinned host slots for the few hundred bytes a call uploads (lengths + mask rectangles):
-    one asynchronous H2D per forward instead of several pageable copies.  A slot is reused only after
-    the event recorded behind its copy has completed."""
+    """Rings of pinned host slots for the few hundred bytes a call uploads (lengths + mask rectangles / uniforms):
+    one asynchronous H2D per forward instead of several pageable copies.  One ring PER DEVICE (DataParallel
+    replicas share the module's attributes, and a CUDA event belongs to the device it was first recorded on);
+    slot selection, growth and reuse all happen under the lock.  A slot is reused only after the event recorded
+    behind its copy has completed."""
 
     def __init__(self, slots: int = 16, nbytes: int = 1 << 14):
         self._nslots, self._nbytes = slots, nbytes
-        self._slots = None  # pinned memory needs a driver: allocate on first use
-        self._np = None     # numpy views of the slots
-        self._events = [None] * slots
-        self._next = 0
+        self._rings = {}  # device index -> {"slots": [...], "np": [...], "events": [...], "next": int}
         self._lock = threading.Lock()
+
+    def _ring(self, index: int) -> dict:
+        ring = self._rings.get(index)
+        if ring is None:  # pinned memory needs a driver: allocate on first use
+            slots = [torch.empty(self._nbytes, dtype=torch.uint8).pin_memory() for _ in range(self._nslots)]
+            ring = {"slots": slots, "np": [t.numpy() for t in slots], "events": [None] * self._nslots, "next": 0}
+            self._rings[index] = ring
+        return ring
 
     def upload(self, arrays, device: torch.device, stream=None) -> Tuple[torch.Tensor, list]:
         """arrays: list of contiguous numpy arrays (8-byte aligned sizes handled here).
         Returns (device uint8 tensor keeping the memory alive, list of device pointers)."""
         sizes = [(a.nbytes + 7) & ~7 for a in arrays]
         total = sum(sizes)
+        index = device.index if device.index is not None else torch.cuda.current_device()
         with self._lock:
-            if self._slots is None:
-                self._slots = [torch.empty(self._nbytes, dtype=torch.uint8).pin_memory() for _ in range(self._nslots)]
-                self._np = [t.numpy() for t in self._slots]
-            i = self._next
-            self._next = (i + 1) % len(self._slots)
-        if total > self._slots[i].numel():
-            self._slots[i] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
-            self._np[i] = self._slots[i].numpy()
-        if self._events[i] is not None:
-            self._events[i].synchronize()
-        host = self._np[i]
+            ring = self._ring(index)
+            i = ring["next"]
+            ring["next"] = (i + 1) % self._nslots
+            if total > ring["slots"][i].numel():
+                ring["slots"][i] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
+                ring["np"][i] = ring["slots"][i].numpy()
+            ev = ring["events"][i]
+            if ev is None:
+                with torch.cuda.device(index):
+                    ev = ring["events"][i] = torch.cuda.Event()
+                first = True
+            else:
+                first = False
+            slot, host = ring["slots"][i], ring["np"][i]
+        if not first:
+            ev.synchronize()  # the copy that last used this slot has left the host buffer
         offs, o = [], 0
         for a, sz in zip(arrays, sizes):
             host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
             offs.append(o)
             o += sz
         dev = torch.empty(total, dtype=torch.uint8, device=device)
-        dev.copy_(self._slots[i][:total], non_blocking=True)
-        if self._events[i] is None:
-            self._events[i] = torch.cuda.Event()
-        self._events[i].record(stream if stream is not None else torch.cuda.current_stream(device))
+        dev.copy_(slot[:total], non_blocking=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream(device))
         base = dev.data_ptr()
         return dev, [base + x for x in offs]
