@@ -222,9 +222,17 @@ class Group:
         self.pa = (_capi.SplPostArgs * self.n)()
         self.keep = []
         self.post = mode == "full" and (conf["cmvn"] != "none" or sa is not None)
+        # one contiguous fp64 buffer for the group's per-utterance sums: the library zeroes it with ONE memset
+        tot_b = sum(it["wav"].shape[0] for it in items)
+        stats_all = torch.empty((tot_b, 2, h.d_out), dtype=torch.float64, device=items[0]["wav"].device)
+        self.keep.append(stats_all)
+        b0 = 0
         for k, it in enumerate(items):
+            nb = it["wav"].shape[0]
+            st = stats_all[b0:b0 + nb]
+            b0 += nb
             self.keep.append(h._fill_args(self.fa[k], it["wav"], it["lens"], it["T"], None, 0,
-                                          it["stats"] if (need_stats and mode != "stats") else None,
+                                          st if (need_stats and mode != "stats") else None,
                                           global_stats if mode == "stats" else None, it["feats"], it["flen"]))
             a = self.pa[k]
             a.Dm = h.d_out

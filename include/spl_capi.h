@@ -171,8 +171,9 @@ SPL_API int spl_tc_selftest(const float* A, const float* B, float* D, int32_t N,
 /* kernel-A engine a call with this sample format runs on: "umma" (tcgen05 DFT-as-GEMM), "fft", "simple" */
 SPL_API const char* spl_engine_name(const spl_handle* h, int32_t sample_format);
 /* Host-only (no device needed): the tcgen05 engine's tables for a configuration, for the CPU model of the kernel
- * in tests/ (tools/emulate_umma.py).  fmt 0 = fp32 samples, 1 = int16.  info[11] = {supported, twiddle bytes, table
- * floats, offset of the mel weights, offset of the shift codes, trailing emits, epilogue parts, first filter of part 0..3}.  Buffers may be NULL to query sizes. */
+ * in tests/ (tools/emulate_umma.py).  fmt 0 = fp32 samples, 1 = int16.  info[16] = {supported, twiddle bytes, table
+ * floats, offset of the mel weights, offset of the shift codes, trailing emits, epilogue parts, first filter of part 0..3,
+ * first step of part 0..4}.  Buffers may be NULL to query sizes. */
 SPL_API int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* window, const float* mel_dense,
                                   int32_t fmt, void* twiddles, size_t twiddle_cap, float* tab, size_t tab_cap,
                                   int32_t* info);

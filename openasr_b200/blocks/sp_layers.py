@@ -259,6 +259,9 @@ class SPLayer(nn.Module):
         outs, alive = [], [keep]
         ai = 0
         do_post = self._cmvn != "none" or aug
+        # one contiguous fp64 buffer for the per-utterance sums of all batches: the library zeroes it with one memset
+        stats_all = torch.empty((sum(m[2] for m in meta), 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
+        sb0 = 0
         for k, (wav_batch, lens_dev, B, T, uni_idx) in enumerate(meta):
             if lens_dev is None:
                 lens_ptr = ptrs[ai]
@@ -269,9 +272,10 @@ class SPLayer(nn.Module):
                 ai += 1
             feats = torch.empty((B, T, h.d_out), dtype=torch.float32, device=dev)
             feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
-            utt_stats = torch.empty((B, 2, h.d_out), dtype=torch.float64, device=dev) if need_stats else None
+            utt_stats = stats_all[sb0:sb0 + B] if need_stats else None
+            sb0 += B
             alive.append(h._fill_args(fa[k], wav_batch, lens_ptr, T, None, seed, utt_stats, None, feats, feat_len))
-            alive.append(utt_stats)
+            alive.append(stats_all)
             if do_post:
                 a = pa[k]
                 a.Dm = h.d_out

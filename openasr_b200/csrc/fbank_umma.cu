@@ -127,20 +127,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // Bounded wait: a protocol error must not hang the GPU.  Returns false on timeout or when another role aborted.
-__device__ __forceinline__ bool mbar_wait_or_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code = 0) {
-  const uint32_t addr = smem_u32(bar);
+// The first polls are back to back (the common case: the phase is complete or about to be); after that the warp
+// sleeps between polls so that waiting roles do not take issue slots from the working ones.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity, volatile int* abort_flag, int code) {
   unsigned long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(2000u)  // suspend-time hint (ns): a waiting warp sleeps instead of polling
-        : "memory");
-    if (done) return true;
-    if ((it & 63u) == 63u) {
+    if (mbar_try(addr, parity)) return true;
+    __nanosleep(it < 16 ? 32 : 128);
+    if ((it & 255u) == 255u) {
       if (*abort_flag) return false;
       const unsigned long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -150,6 +155,20 @@ __device__ __forceinline__ bool mbar_wait_or_abort(uint64_t* bar, uint32_t parit
       }
     }
   }
+}
+__device__ __forceinline__ bool mbar_wait_or_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code = 0) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try(addr, parity)) return true;
+  if (mbar_try(addr, parity)) return true;
+  return mbar_wait_slow(addr, parity, abort_flag, code);
+}
+
+// A wait every worker warp needs: warp 0 polls the mbarrier, the other fifteen block on a hardware named barrier
+// (no issue slots) until warp 0 joins it.  16 polling warps cost 37 % of all issued instructions (ncu, profiles/).
+__device__ __forceinline__ bool workers_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code, int w) {
+  if (w == 0) mbar_wait_or_abort(bar, parity, abort_flag, code);
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  return *abort_flag == 0;
 }
 
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -173,6 +192,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// fp64 add to global memory without a return value (SASS RED): the warp does not wait for the L2 round trip
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -364,7 +387,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         }
       }
     }
-    if (!mbar_wait_or_abort(bars + BAR_TAB, 0, abort_flag, BAR_TAB | (w << 8))) goto done;
+    if (!workers_wait(bars + BAR_TAB, 0, abort_flag, BAR_TAB | (w << 8), w)) goto done;
     {
       const int rl = lane >> 2, q = lane & 3;   // row inside the warp, octet inside the chunk
       const int row = 8 * w + rl;
@@ -373,12 +396,15 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
       uint32_t chunk_seq = 0;                   // A stages used so far
       for (int tile = 0;; ++tile) {
         const int slot = tile & 1;
-        if (!mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8))) goto done;
+        if (w == 0) mbar_wait_or_abort(bars + BAR_READY + slot, (tile >> 1) & 1, abort_flag, BAR_READY | (w << 8));
         RowTab& rt = rtab[slot];
+        if (w == 0 && !*abort_flag && rt.nrows != 0)  // the tile's samples have landed
+          mbar_wait_or_abort(bars + BAR_SFULL, tile & 1, abort_flag, BAR_SFULL | (w << 8));
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (*abort_flag) goto done;
         const int nrows = rt.nrows;
         if (nrows == 0) break;
         UTR(1);
-        if (!mbar_wait_or_abort(bars + BAR_SFULL, tile & 1, abort_flag, BAR_SFULL | (w << 8))) goto done;  // the tile's samples have landed
         UTR(2);
         const bool rvalid = row < nrows;
         // rows past the tile's end mirror the warp's first row (finite data, results never stored)
@@ -465,7 +491,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         for (int c = 0; c <= NCH; ++c, ++chunk_seq) {
           const int st = chunk_seq & 1;
           uint8_t* stage = sm + L.off_a + st * L.a_stage;
-          if (chunk_seq >= 2 && !mbar_wait_or_abort(bars + BAR_AEMPTY + st, ((chunk_seq >> 1) - 1) & 1, abort_flag, BAR_AEMPTY | (w << 8))) goto done;
+          if (chunk_seq >= 2 && !workers_wait(bars + BAR_AEMPTY + st, ((chunk_seq >> 1) - 1) & 1, abort_flag, BAR_AEMPTY | (w << 8), w)) goto done;
           UTR(10 + c);
           // byte offset of this lane's 8-byte slice (K columns 4q..4q+3) inside a sub-tile (SWIZZLE_32B)
           const uint32_t aoff = (uint32_t)(row * 32 + ((((q >> 1) ^ (row >> 2)) & 1) << 4) + ((q & 1) << 3));
@@ -592,7 +618,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
         }
 
         // ---- epilogue of this tile, all workers: warp = (TMEM lane quarter eq, bin part pt) --------------------
-        if (!mbar_wait_or_abort(bars + BAR_TFULL, tile & 1, abort_flag, BAR_TFULL | (w << 8))) goto done;
+        if (!workers_wait(bars + BAR_TFULL, tile & 1, abort_flag, BAR_TFULL | (w << 8), w)) goto done;
         tc::fence_after_sync();
         UTR(111);
         {
@@ -605,86 +631,106 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
             const int ut0 = __shfl_sync(0xffffffffu, my_ut, 0);
             const bool one_utt = __all_sync(0xffffffffu, my_ut >= 0 && ((my_ut ^ ut0) & 0xffffff) == 0);
             const bool want_utt = p.want_utt_stats != 0, want_g = p.global_stats != nullptr;
-            // staging [32 rows][17]: this warp's own 256-byte slices of the (idle) A ring -- rows 8w..8w+7 of the 16
-            // sub-tiles, which no other warp writes and the tensor core only reads after this warp's next arrival
+            // staging ring of raw mel energies, 32 column positions x 32 rows: this warp's own 256-byte slices of the
+            // (idle) A ring -- rows 8w..8w+7 of the 16 sub-tiles, which no other warp writes and the tensor core only
+            // reads after this warp's next arrival.  Two positions per slice, row index XOR-skewed by the position so
+            // that both the emit (lane = row, one position) and the flush (lane = 4 rows x 8 positions) are conflict-free
             uint8_t* const stg_base = sm + L.off_a + (w << 8);
-            auto stg = [&](int i) -> float& { return *reinterpret_cast<float*>(stg_base + ((i >> 6) << 12) + ((i & 63) << 2)); };
+            auto stg = [&](int pos, int r) -> float& {
+              return *reinterpret_cast<float*>(stg_base + ((pos >> 1) << 12) + ((pos & 1) << 7) + ((r ^ ((pos & 7) << 2)) << 2));
+            };
             float* const sbuf = reinterpret_cast<float*>(sm + L.off_sb);
-            const int steps_per_part = 2 * HALF / p.nparts;
-            const int s_beg = pt * steps_per_part, s_end = s_beg + steps_per_part;
+            const int s_beg = p.part_s0[pt], s_end = p.part_s0[pt + 1];  // multiples of 8, balanced by cost on the host
             int outc = pt == 0 ? 0 : p.part_f0[pt] + 2;  // next output column this part finalises
-            int pc0 = outc;                              // first column of the piece being staged
+            int pc0 = outc;                              // first column still staged
+            int wpos = 0, rpos = 0;                      // ring positions of outc / pc0
             int emitted = 0;
             float accA = 0.f, accB = 0.f;
-            // store + column sums of the staged piece [c0, c0 + n), n <= 16
-            auto flush_piece = [&](int c0, int n) {
+            // log + store + column sums of the n <= 8 oldest staged columns [pc0, pc0 + n): lane = (4-row group rr, column c)
+            auto flush8 = [&](int n) {
+              UTR(123);
               __syncwarp();
-              const int c = lane & 15, hf = lane >> 4;
-#pragma unroll 4
-              for (int it = 0; it < 16; ++it) {
-                const int r = 2 * it + hf;
-                float* o = rt.out[32 * eq + r];
-                if (c < n && o != nullptr) o[c0 + c] = stg(r * 17 + c);
-              }
-              if ((want_utt || want_g) && c < n) {
-                double s1 = 0.0, s2 = 0.0, g1 = 0.0, g2 = 0.0;
-                int cu = -1;
-                auto push = [&]() {
-                  if (cu >= 0 && want_utt) {
-                    const UBatch& bd = p.bd[batch_of(p, cu)];
-                    if (bd.utt_stats) {
-                      atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + c0 + c, s1);
-                      atomicAdd(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + c0 + c, s2);
-                    }
-                  }
-                  g1 += s1;
-                  g2 += s2;
-                  s1 = s2 = 0.0;
-                };
+              const int c = lane & 7, rr = lane >> 3;
+              const int cp = (rpos + c) & 31;
+              double s1 = 0.0, s2 = 0.0;
+              float f1 = 0.f, f2 = 0.f;  // fp32 partial sums over this warp's 32 rows, accumulated in fp64 across warps
+              if (c < n) {
                 if (one_utt) {
-                  cu = ut0 & 0xffffff;
-                  double t1 = 0.0, t2 = 0.0;  // two independent chains
 #pragma unroll
-                  for (int i = 0; i < 16; i += 2) {
-                    const double v0 = (double)stg((16 * hf + i) * 17 + c), v1 = (double)stg((16 * hf + i + 1) * 17 + c);
-                    s1 += v0;
-                    t1 += v1;
-                    s2 = fma(v0, v0, s2);
-                    t2 = fma(v1, v1, t2);
+                  for (int it = 0; it < 8; ++it) {
+                    const int r = 4 * it + rr;
+                    const float v = fast_log(fmaxf(stg(cp, r), kEps));  // kaldi_signal.py:540
+                    rt.out[32 * eq + r][pc0 + c] = v;
+                    f1 += v;
+                    f2 = fmaf(v, v, f2);
                   }
-                  s1 += t1;
-                  s2 += t2;
-                } else {
-                  for (int i = 0; i < 16; ++i) {
-                    const int r = 16 * hf + i;
-                    const int ut = rt.ut[32 * eq + r];
-                    const int u = ut < 0 ? -1 : (ut & 0xffffff);
+                } else {  // utterance boundaries / rows past the tile's end inside this warp: per-row bookkeeping
+                  int cu = -1;
+                  auto push = [&]() {
+                    if (cu >= 0 && want_utt) {
+                      const UBatch& bd = p.bd[batch_of(p, cu)];
+                      if (bd.utt_stats) {
+                        red_add_f64(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + pc0 + c, s1);
+                        red_add_f64(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + pc0 + c, s2);
+                      }
+                    }
+                    if (cu >= 0 && want_g) {
+                      atomicAdd(gst + pc0 + c, s1);
+                      atomicAdd(gst + D_out + pc0 + c, s2);
+                    }
+                    s1 = s2 = 0.0;
+                  };
+                  for (int it = 0; it < 8; ++it) {
+                    const int r = 4 * it + rr;
+                    float* o = rt.out[32 * eq + r];
+                    if (o == nullptr) continue;
+                    const float v = fast_log(fmaxf(stg(cp, r), kEps));
+                    o[pc0 + c] = v;
+                    const int u = rt.ut[32 * eq + r] & 0xffffff;
                     if (u != cu) {
                       push();
                       cu = u;
                     }
-                    if (u >= 0) {
-                      const double v = (double)stg(r * 17 + c);
-                      s1 += v;
-                      s2 = fma(v, v, s2);
+                    const double d = (double)v;
+                    s1 += d;
+                    s2 = fma(d, d, s2);
+                  }
+                  push();
+                }
+              }
+              UTR(124);
+              if (one_utt && (want_utt || want_g)) {  // reduce the four row groups, one atomic per column
+#pragma unroll
+                for (int o = 8; o < 32; o <<= 1) {
+                  f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                  f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+                }
+                s1 = (double)f1;
+                s2 = (double)f2;
+                if (rr == 0 && c < n) {
+                  if (want_utt) {
+                    const int cu = ut0 & 0xffffff;
+                    const UBatch& bd = p.bd[batch_of(p, cu)];
+                    if (bd.utt_stats) {
+                      red_add_f64(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 0) * D_out + pc0 + c, s1);
+                      red_add_f64(bd.utt_stats + ((size_t)(cu - bd.u0) * 2 + 1) * D_out + pc0 + c, s2);
                     }
                   }
-                }
-                push();
-                if (want_g) {
-                  atomicAdd(gst + c0 + c, g1);
-                  atomicAdd(gst + D_out + c0 + c, g2);
+                  if (want_g) {
+                    atomicAdd(gst + pc0 + c, s1);
+                    atomicAdd(gst + D_out + pc0 + c, s2);
+                  }
                 }
               }
+              pc0 += n;
+              rpos = (rpos + n) & 31;
               __syncwarp();
+              UTR(125);
             };
-            auto finalise = [&](float e) {
-              stg(lane * 17 + (outc - pc0)) = fast_log(fmaxf(e * inv2, kEps));  // kaldi_signal.py:540
+            auto finalise = [&](float e) {  // stage the raw energy; the log is taken lane-parallel in flush8
+              stg(wpos, lane) = e * inv2;
               ++outc;
-              if (outc - pc0 == 16) {
-                flush_piece(pc0, 16);
-                pc0 = outc;
-              }
+              wpos = (wpos + 1) & 31;
             };
             // A filter is complete: parts above the first hand their first two (cut by the part boundary) to the
             // part below as raw partial sums; everything else is finalised here
@@ -715,6 +761,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
             }
 #pragma unroll 1
             for (int step0 = s_beg; step0 < s_end; step0 += 8) {
+              UTR(120);
               // pass 1 (step < HALF): bin = step + 1 = column + 1;  pass 2: bin = HALF + i, column = HALF - 1 - i
               const bool second = step0 >= HALF;
               const int c0 = second ? (2 * HALF - 8 - step0) : step0;  // first TMEM column of the 8 read here
@@ -736,6 +783,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
               }
               const uint32_t ctl = (melc[step0 >> 4] >> ((step0 & 8) << 1)) & 0xffffu;
               tmem_ld_wait();
+              UTR(121);
               float pw[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -750,6 +798,23 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
                   accA = fmaf(wv[i].x, pw[i], accA);
                   accB = fmaf(wv[i].y, pw[i], accB);
                 }
+              } else if ((ctl & 0xaaaau) == 0u && (pt == 0 || emitted >= 2)) {
+                // at most one filter ends per bin and none of them is handed down: straight-line, predicated
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const bool pe = ((ctl >> (2 * i)) & 1u) != 0u;  // uniform
+                  stg(wpos, lane) = accA * inv2;  // unconditional: the slot is rewritten until a filter really ends
+                  wpos = (wpos + (pe ? 1 : 0)) & 31;
+                  outc += pe ? 1 : 0;
+                  emitted += pe ? 1 : 0;
+                  accA = pe ? accB : accA;
+                  accB = pe ? 0.f : accB;
+                  accA = fmaf(wv[i].x, pw[i], accA);
+                  accB = fmaf(wv[i].y, pw[i], accB);
+                }
+                UTR(122);
+#pragma unroll 1
+                while (outc - pc0 >= 8) flush8(8);
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -761,6 +826,9 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
                   accA = fmaf(wv[i].x, pw[i], accA);
                   accB = fmaf(wv[i].y, pw[i], accB);
                 }
+                UTR(122);
+#pragma unroll 1
+                while (outc - pc0 >= 8) flush8(8);  // at most 16 emits per iteration (host-checked): the ring holds 24
               }
             }
             // this warp's share of the accumulators is drained: the next tile's MMAs may overwrite them
@@ -770,14 +838,16 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
             UTR(130);
             if (pt + 1 < p.nparts) {
               // the two filters cut by the upper boundary: this part's tail + the head sums of the part above
-              if (!mbar_wait_or_abort(bars + BAR_SB + pt * 4 + eq, tile & 1, abort_flag, BAR_SB | (w << 8))) goto done;
+              // (on a timeout the abort flag is set and every worker leaves together at its next common wait)
+              mbar_wait_or_abort(bars + BAR_SB + pt * 4 + eq, tile & 1, abort_flag, BAR_SB | (w << 8));
               const float v0 = accA + sbuf[(pt * kURows + erow) * 2 + 0], v1 = accB + sbuf[(pt * kURows + erow) * 2 + 1];
               finalise(v0);
               finalise(v1);
             } else {
               for (int i = 0; i < p.nflush; ++i) emit();
             }
-            if (outc > pc0) flush_piece(pc0, outc - pc0);
+#pragma unroll 1
+            while (outc > pc0) flush8(outc - pc0 < 8 ? outc - pc0 : 8);
             if (want_g && w == 0 && lane == 0) atomicAdd(gcount, nrows);
           } else {
             tc::fence_before_sync();
@@ -813,13 +883,17 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
             if (!mbar_wait_or_abort(bars + BAR_BFULL + bs, (hs_seq / kBStages) & 1, abort_flag, BAR_BFULL | (w << 8))) { ok = false; break; }
             tc::fence_after_sync();
             const uint32_t b_st = b_base + bs * L.b_stage;
+            // descriptors: constant fields | (address >> 4); sub-tiles are reached by integer adds (no carries:
+            // shared-memory addresses are below 2^18)
+            const uint64_t ad0 = tc::make_desc_sw32(a_st), bd0 = tc::make_desc_sw32(b_st);
+            const uint64_t a_step = (uint64_t)(L.a_sub >> 4), b_step = (uint64_t)(L.b_tile >> 4);
             if (c < NCH) {
 #pragma unroll
               for (int pp = 0; pp < 2; ++pp) {  // even / odd block of this half (cos: 0, 1; sin: 2, 3)
                 const int blk = 2 * hf + pp;
                 const int asub = (hf == 1 && !mirror) ? 2 * pp : 2 * blk;  // no mirror: b == a, reuse the cos operand
-                const uint64_t ahi = tc::make_desc_sw32(a_st + asub * L.a_sub), alo = tc::make_desc_sw32(a_st + (asub + 1) * L.a_sub);
-                const uint64_t bhi = tc::make_desc_sw32(b_st + (2 * pp) * L.b_tile), blo = tc::make_desc_sw32(b_st + (2 * pp + 1) * L.b_tile);
+                const uint64_t ahi = ad0 + a_step * asub, alo = ahi + a_step;
+                const uint64_t bhi = bd0 + b_step * (2 * pp), blo = bhi + b_step;
                 const uint32_t d = tmem + blk * HALF;
                 mma_f16(d, ahi, bhi, idesc, c > 0);
                 mma_f16(d, alo, bhi, idesc, 1);
@@ -830,8 +904,7 @@ __global__ void __launch_bounds__(kUThreads, 1) fbank_umma_kernel(const __grid_c
               for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
                 for (int kx = 0; kx < KX; ++kx)
-                  mma_f16(tmem + (2 * hf + pp) * HALF, tc::make_desc_sw32(a_st + kx * L.a_sub),
-                          tc::make_desc_sw32(b_st + (kx * 2 + pp) * L.b_tile), idesc, 1);
+                  mma_f16(tmem + (2 * hf + pp) * HALF, ad0 + a_step * kx, bd0 + b_step * (kx * 2 + pp), idesc, 1);
             }
             tc::commit(bars + BAR_BEMPTY + bs);
           }

@@ -62,7 +62,7 @@ struct spl_handle {
   bool umma_ok[2];
   const uint8_t* umma_tw[2];
   const float* umma_tab[2];
-  int umma_tab_bytes[2], umma_off_melw[2], umma_off_melc[2], umma_nflush, umma_nparts, umma_part_f0[4];
+  int umma_tab_bytes[2], umma_off_melw[2], umma_off_melc[2], umma_nflush, umma_nparts, umma_part_f0[4], umma_part_s0[5];
   int umma_ctas;     // grid of the tcgen05 engine (SM count; SPL_UMMA_CTAS overrides, diagnostics)
 };
 
@@ -251,6 +251,7 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->umma_nflush = ut.nflush;
   h->umma_nparts = ut.nparts;
   for (int i = 0; i < 4; ++i) h->umma_part_f0[i] = ut.part_f0[i];
+  for (int i = 0; i < 5; ++i) h->umma_part_s0[i] = ut.part_s0[i];
   for (int f = 0; f < 2; ++f) {
     h->umma_ok[f] = ut.ok && !ut.tab[f].empty();
     h->umma_tab[f] = fb + o_utab[f];
@@ -390,6 +391,7 @@ cudaError_t launch_umma(spl_handle* h, const spl_fbank_args* v, int n, cudaStrea
   p.nflush = h->umma_nflush;
   p.nparts = h->umma_nparts;
   for (int i = 0; i < 4; ++i) p.part_f0[i] = h->umma_part_f0[i];
+  for (int i = 0; i < 5; ++i) p.part_s0[i] = h->umma_part_s0[i];
   p.global_stats = v[0].global_stats;
   p.status = h->status;
   p.debug_acc = h->debug_acc;
@@ -509,6 +511,7 @@ int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* wind
   info[5] = ut.nflush;
   info[6] = ut.nparts;
   for (int i = 0; i < 4; ++i) info[7 + i] = ut.part_f0[i];
+  for (int i = 0; i < 5; ++i) info[11 + i] = ut.part_s0[i];
   if (!info[0]) return SPL_OK;
   if (twiddles && twiddle_cap >= ut.twiddles[fmt].size()) std::memcpy(twiddles, ut.twiddles[fmt].data(), ut.twiddles[fmt].size());
   if (tab && tab_cap >= ut.tab[fmt].size()) std::memcpy(tab, ut.tab[fmt].data(), ut.tab[fmt].size() * 4);

@@ -116,7 +116,8 @@ struct UmmaParams {
   float preemph, dither;
   uint32_t seed_lo, seed_hi;
   int32_t nb, total_utts, nflush, want_utt_stats;
-  int32_t nparts, part_f0[4];  // epilogue: bin parts (1, 2 or 4) and the filter the running sums start on in each part
+  int32_t nparts, part_f0[4], part_s0[5];  // epilogue: bin parts (1, 2 or 4): first step (multiple of 8) and the filter
+                                           // the running sums start on in each part
   double* global_stats;
   int32_t* status;          // device word: 0x10000 | barrier | warp << 8 of the first barrier wait that timed out
   float* debug_acc;         // diagnostics: raw accumulators of tile 0 of CTA 0, [128][4 HALF + 1], or NULL
@@ -133,7 +134,7 @@ size_t fbank_umma_smem_bytes(int nfft, int es, int tab_bytes, int D_out);
 struct UmmaHostTables {
   bool ok = false;
   int nflush = 0;
-  int nparts = 1, part_f0[4] = {0, 0, 0, 0};
+  int nparts = 1, part_f0[4] = {0, 0, 0, 0}, part_s0[5] = {0, 0, 0, 0, 0};
   int off_melw[2] = {0, 0}, off_melc[2] = {0, 0};  // float offsets inside tab[fmt]
   std::vector<uint8_t> twiddles[2];  // [0] fp32 samples (4 shifts), [1] int16 samples (8 shifts)
   std::vector<float> tab[2];

@@ -62,6 +62,11 @@ void build_umma_tables(int nfft, int Nw, int D, const float* window, const float
     melw[2 * s + 1] = fA + 1 < D ? mel_dense[(size_t)(fA + 1) * nb + bin] : 0.f;
   }
   out.nflush = D - fA;
+  for (int s0 = 0; s0 < nb; s0 += 8) {  // the epilogue's staging ring holds 24 columns and is drained per 8 steps
+    int e = 0;
+    for (int s = s0; s < s0 + 8; ++s) e += (int)((melc[s >> 4] >> (2 * (s & 15))) & 3u);
+    if (e > 16) return;
+  }
   {  // the program must reproduce the dense bank exactly (same weights, same filters)
     std::vector<double> P(nb), E(D, 0.0), ref(D, 0.0);
     for (int b = 0; b < nb; ++b) P[b] = 1.0 + 0.37 * b + (double)((b * 2654435761u) % 97u);
@@ -88,23 +93,42 @@ void build_umma_tables(int nfft, int Nw, int D, const float* window, const float
       if (std::fabs(E[m] - ref[m]) > 1e-9 * (1.0 + std::fabs(ref[m]))) return;
   }
 
-  // epilogue parts: the steps are split evenly over 4 (or 2, or 1) warps per TMEM lane quarter; a part above the
-  // first hands its first two emitted filters to the part below, so it needs at least two emits of its own
+  // epilogue parts: the steps are split over 4 (or 2, or 1) warps per TMEM lane quarter at multiples of 8, balanced
+  // by cost (an 8-step iteration ~ 1 unit, 8 finished filters ~ 1.5 units: log, store, column sums); a part above
+  // the first hands its first two emitted filters to the part below, so it needs at least two emits of its own
   out.nparts = 1;
-  for (int np = 4; np >= 2 && out.nparts == 1; np >>= 1) {
-    const int spp = nb / np;
-    bool ok = spp % 8 == 0;
-    int f = 0, f0[4] = {0, 0, 0, 0};
-    for (int pt = 0; pt < np && ok; ++pt) {
-      f0[pt] = f;
-      int emits = 0;
-      for (int s = pt * spp; s < (pt + 1) * spp; ++s) emits += (int)((melc[s >> 4] >> (2 * (s & 15))) & 3u);
-      f += emits;
-      if (pt > 0 && emits < 2) ok = false;
+  out.part_s0[0] = 0;
+  out.part_s0[1] = nb;
+  {
+    const int ng = nb / 8;
+    std::vector<int> ge(ng, 0);
+    std::vector<double> cum(ng + 1, 0.0);
+    for (int g = 0; g < ng; ++g) {
+      for (int s = 8 * g; s < 8 * g + 8; ++s) ge[g] += (int)((melc[s >> 4] >> (2 * (s & 15))) & 3u);
+      cum[g + 1] = cum[g] + 1.0 + 1.5 * ge[g] / 8.0;
     }
-    if (ok) {
-      out.nparts = np;
-      for (int pt = 0; pt < 4; ++pt) out.part_f0[pt] = f0[pt];
+    for (int np = 4; np >= 2 && out.nparts == 1; np >>= 1) {
+      int g0[5] = {0, 0, 0, 0, 0};
+      g0[np] = ng;
+      for (int pt = 1; pt < np; ++pt) {
+        int g = g0[pt - 1] + 1;
+        while (g < ng - (np - pt) && cum[g] < cum[ng] * pt / np) ++g;
+        g0[pt] = g;
+      }
+      bool ok = true;
+      int f = 0, f0[4] = {0, 0, 0, 0};
+      for (int pt = 0; pt < np && ok; ++pt) {
+        f0[pt] = f;
+        int emits = 0;
+        for (int g = g0[pt]; g < g0[pt + 1]; ++g) emits += ge[g];
+        f += emits;
+        if (g0[pt + 1] <= g0[pt] || (pt > 0 && emits < 2)) ok = false;
+      }
+      if (ok) {
+        out.nparts = np;
+        for (int pt = 0; pt < 4; ++pt) out.part_f0[pt] = f0[pt];
+        for (int pt = 0; pt <= np; ++pt) out.part_s0[pt] = 8 * g0[pt];
+      }
     }
   }
 

@@ -59,11 +59,12 @@ def test_mel_program_and_parts():
         shifts = [(int(melc[s >> 4]) >> (2 * (s & 15))) & 3 for s in range(NB)]
         assert sum(shifts) + T["nflush"] == D
         assert T["nparts"] in (1, 2, 4)
-        spp = NB // T["nparts"]
+        s0 = T["part_s0"]
+        assert s0[0] == 0 and s0[T["nparts"]] == NB and all(v % 8 == 0 for v in s0[:T["nparts"] + 1])
         f = 0
         for pt in range(T["nparts"]):
-            assert T["part_f0"][pt] == f
-            e = sum(shifts[pt * spp:(pt + 1) * spp])
+            assert T["part_f0"][pt] == f and s0[pt + 1] > s0[pt]
+            e = sum(shifts[s0[pt]:s0[pt + 1]])
             assert pt == 0 or e >= 2
             f += e
 

@@ -38,7 +38,7 @@ def load_tables(sr, D, fmt=0, window="povey"):
     S, Nw, N = tables.frame_geometry(sr)
     win = tables.window_table(window, Nw).to(torch.float32).contiguous()
     mel = tables.mel_table(D, N, sr).to(torch.float32).contiguous()
-    info = (C.c_int32 * 11)()
+    info = (C.c_int32 * 16)()
     _capi.check(lib.spl_debug_umma_tables(N, Nw, D, C.c_void_p(win.data_ptr()), C.c_void_p(mel.data_ptr()), fmt,
                                           None, 0, None, 0, info), "spl_debug_umma_tables")
     if not info[0]:
@@ -50,7 +50,7 @@ def load_tables(sr, D, fmt=0, window="povey"):
                 "spl_debug_umma_tables")
     return {"N": N, "Nw": Nw, "S": S, "D": D, "nshift": 4 if fmt == 0 else 8, "tw": tw, "tab": tab,
             "off_melw": info[3], "off_melc": info[4], "nflush": info[5], "nparts": info[6],
-            "part_f0": [info[7 + i] for i in range(4)]}
+            "part_f0": [info[7 + i] for i in range(4)], "part_s0": [info[11 + i] for i in range(5)]}
 
 
 def _tile(tw, off, rows):

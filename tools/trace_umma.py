@@ -32,7 +32,7 @@ buf = buf.reshape(23, 512)
 t00 = min(int(buf[w, 0]) & 0xffffffffffff for w in range(23))
 names = {0: "start", 1: "P ready", 2: "P samples", 3: "P pass1", 40: "M tmem-empty", 100: "S built", 101: "S samples-free",
          102: "S tma-issued", 103: "S published", 110: "E ready", 111: "E tmem-full", 130: "E tmem-released", 131: "E tile-end", 200: "done"}
-for w in (0, 5, 15, 16, 17, 18):
+for w in (0, 12, 16):
     n = int(buf[w, 511])
     print("---- warp %d (%d stamps)" % (w, n))
     prev = None
@@ -41,10 +41,9 @@ for w in (0, 5, 15, 16, 17, 18):
         v = int(buf[w, i]); tag = v >> 48; t = (v & 0xffffffffffff) - t00
         nm = names.get(tag, ("P c%d start" % (tag - 10) if 10 <= tag < 20 else "P c%d full" % (tag - 20) if 20 <= tag < 30 else
                              "M c%d afull" % (tag - 50) if 50 <= tag < 60 else "M c%d issued" % (tag - 70) if 70 <= tag < 80 else
-                             "T hs" if tag == 90 else "E q%d" % (tag - 120) if 120 <= tag < 130 else str(tag)))
+                             "T hs" if tag == 90 else {120: "E it", 121: "E ld", 122: "E acc", 123: "F in", 124: "F rows", 125: "F out"}.get(tag, str(tag))))
         line.append("%s@%d" % (nm, t))
         if len(line) == 6:
             print("   " + "  ".join(line)); line = []
-        if i > 150 and w not in (16,): break
-        if i > 260: break
+        if i > 130: break
     if line: print("   " + "  ".join(line))
