@@ -100,7 +100,7 @@ SPL_API int spl_fbank_forward(spl_handle* h, const spl_fbank_args* a, void* stre
 /* Several padded batches in ONE persistent launch of kernel A (the per-utterance loop of sp_layers.py:81-91
  * over a queue of batches): `args[0..n)` as for spl_fbank_forward; every batch has its own buffers, lengths
  * and T.  Launch, prologue and tail are paid once, and the frames of all batches are balanced over the SMs
- * together.  Up to 8 batches / 512 utterances share a launch; larger calls are split transparently.
+ * together.  Up to 16 batches / 512 utterances share a launch; larger calls are split transparently.
  * dither_seed and global_stats are taken from the first batch of each launch. */
 SPL_API int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n, void* stream);
 
@@ -177,6 +177,10 @@ SPL_API const char* spl_engine_name(const spl_handle* h, int32_t sample_format);
 SPL_API int spl_debug_umma_tables(int32_t nfft, int32_t Nw, int32_t D, const float* window, const float* mel_dense,
                                   int32_t fmt, void* twiddles, size_t twiddle_cap, float* tab, size_t tab_cap,
                                   int32_t* info);
+/* Diagnostics: the unit-dither noise g[b, t, j] (B x T x window_size floats, device) the FFT engine's device RNG adds
+ * for `seed` -- the same Philox stream, sample by sample -- so tests can check the noise itself against the
+ * reference's rand_gauss (kaldi_signal.py:174-178) and replay it through the host-noise mode. */
+SPL_API int spl_debug_dither_noise(spl_handle* h, float* out, int32_t B, int32_t T, uint64_t seed, void* stream);
 /* SYNCHRONOUS diagnostics: raw tcgen05 accumulators [128][4*Nfft/4 + 1] of the first tile (handle created with
  * SPL_UMMA_DEBUG=1 in the environment) */
 SPL_API int spl_debug_umma_acc(spl_handle* h, float* host_out, size_t n_floats);

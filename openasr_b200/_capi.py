@@ -73,7 +73,7 @@ class SplPostArgs(C.Structure):
 
 EXPORTS = ("spl_create", "spl_destroy", "spl_fbank_forward", "spl_post_inplace", "spl_column_stats",
            "spl_feature_dim", "spl_abi_version", "spl_last_error", "spl_launch_count", "spl_tc_selftest", "spl_specaug_rects",
-           "spl_conv0_relu", "spl_fbank_forward_multi", "spl_engine_name", "spl_debug_status", "spl_debug_umma_tables", "spl_debug_umma_acc", "spl_post_inplace_multi", "spl_forward_multi")
+           "spl_conv0_relu", "spl_fbank_forward_multi", "spl_engine_name", "spl_debug_status", "spl_debug_umma_tables", "spl_debug_umma_acc", "spl_post_inplace_multi", "spl_forward_multi", "spl_debug_dither_noise")
 
 _lib = None
 
@@ -101,6 +101,8 @@ def load() -> C.CDLL:
     lib.spl_engine_name.restype = C.c_char_p
     lib.spl_debug_status.argtypes = [C.c_void_p]
     lib.spl_debug_status.restype = C.c_int
+    lib.spl_debug_dither_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]
+    lib.spl_debug_dither_noise.restype = C.c_int
     lib.spl_debug_umma_acc.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.spl_debug_umma_acc.restype = C.c_int
     lib.spl_debug_umma_tables.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -1,0 +1,32 @@
+// Diagnostics that are not on the hot path: the device dither generator written out sample by sample, so that
+// tests can check the noise ITSELF (moments, range, independence across overlapping frames) against the
+// reference's rand_gauss (kaldi_signal.py:174-178) and feed it back through the host-noise mode.
+#include "fbank_frame.cuh"
+
+namespace spl {
+
+// Same stream as load_frame_pair's device-RNG branch (fbank_frame.cuh): the noise of (utterance b, frame t,
+// sample j = R2 n1 + n2) is the (n1 % 8)-th 16-bit word of Philox4x32-7(ctr = ((n1 / 8) R2 + n2, t, b, 0x5eed), key = seed).
+__global__ void dither_noise_kernel(float* __restrict__ out, int B, int T, int Nw, int R2, uint32_t seed_lo, uint32_t seed_hi) {
+  const size_t n = (size_t)B * T * Nw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Nw);
+    const int t = (int)((i / Nw) % T), b = (int)(i / ((size_t)Nw * T));
+    const int n1 = j / R2, n2 = j - n1 * R2;
+    const uint4 r = philox4x32_7(make_uint4((uint32_t)((n1 >> 3) * R2 + n2), (uint32_t)t, (uint32_t)b, 0x5eedu), seed_lo, seed_hi);
+    const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+    const int k = n1 & 7;
+    const float u = (float)((k & 1) ? (wd[k >> 1] >> 16) : (wd[k >> 1] & 0xffffu)) + 0.5f;
+    const float a = fmaf(fast_log2(u), -1.3862943611198906f, 16.0001f * 1.3862943611198906f);
+    float cs;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(u * 9.587379924285257e-05f));
+    out[i] = fast_sqrt(a) * cs;
+  }
+}
+
+cudaError_t launch_dither_noise(float* out, int B, int T, int Nw, int R2, uint64_t seed, cudaStream_t st) {
+  dither_noise_kernel<<<592, 256, 0, st>>>(out, B, T, Nw, R2, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  return cudaGetLastError();
+}
+
+}  // namespace spl

@@ -56,20 +56,6 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint32_t k0, uint32_t k
   return ctr;
 }
 
-// dither * g(u) for a 24-bit uniform v = u * 2^24 (kaldi_signal.py:176-177):
-//   x = max(eps, u) (eps = 2^-23 <=> v >= 2),  g = sqrt(-2 ln x) * cos(2 pi x).
-// d2 = dither^2 folded under the square root.
-__device__ __forceinline__ float dither_term(uint32_t v24, float d2) {
-  const float v = (float)max(v24, 2u);
-  // -2 ln(v 2^-24) = (24 - lg2 v) * 2 ln 2
-  // the two products are rounded separately: for dither values that are not powers of two `a` can come out
-  // slightly negative at lg2 v == 24 (v >= 2^24 - 11) -> clamp, sqrt.approx of a negative is NaN
-  const float a = fmaxf(fmaf(fast_log2(v), -1.3862943611198906f * d2, 33.27106466687737f * d2), 0.f);
-  float cs;
-  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(v * 3.7450703370559213e-07f));  // 2 pi 2^-24
-  return fast_sqrt(a) * cs;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Compile-time frame geometry: lane n2 of the stage-1 layout holds samples j = R2*n1 + n2.
 template <int NFFT, int NW>
@@ -89,88 +75,6 @@ __device__ __forceinline__ bool row_valid(int n1, int n2, int Nw) {
   return F::R2 * n1 + n2 < Nw;
 }
 
-// One frame in the stage-1 register layout.  kaldi_signal.py:174-199:
-// dither -> DC removal -> raw log-energy -> pre-emphasis -> window.
-//   z_j = w_j * ((x_j - mu) - c (x_{j-1} - mu)) = w_j * (x_j - c x_{j-1} - (1-c) mu),  x_{-1} := x_0
-template <int NFFT, int NW, bool NOISE>
-__device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& p, const float* fr /*frame's first sample*/,
-                                             const float* win, float* energy_slot, int n2, int b, int t, bool valid) {
-  using G = Geo<NFFT>;
-  using F = FG<NFFT, NW>;
-  const int Nw = F::kStatic ? NW : p.Nw;
-  float x[F::NROW];
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) x[n1] = row_valid<NFFT, NW>(n1, n2, Nw) ? fr[G::R2 * n1 + n2] : 0.f;
-
-  if constexpr (NOISE) {
-    if (valid) {
-      if (p.noise != nullptr) {  // parity mode: host-drawn rand_gauss, [B, T, Nw]
-        const float* nz = p.noise + ((size_t)b * p.T + t) * Nw;
-#pragma unroll
-        for (int n1 = 0; n1 < F::NROW; ++n1)
-          if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = fmaf(__ldg(nz + G::R2 * n1 + n2), p.dither, x[n1]);
-      } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call)
-        const float d2 = p.dither * p.dither;
-        const float sgn = p.dither < 0.f ? -1.f : 1.f;
-#pragma unroll
-        for (int c5 = 0; c5 * 5 < F::NROW; ++c5) {
-          const uint4 r = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)t, (uint32_t)b, 0x5eedu),
-                                       p.seed_lo, p.seed_hi);
-          const uint32_t v[5] = {r.x >> 8, r.y >> 8, r.z >> 8, r.w >> 8,
-                                 ((r.x & 0xffu) << 16) | ((r.y & 0xffu) << 8) | (r.z & 0xffu)};
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const int n1 = 5 * c5 + i;
-            if (n1 < F::NROW) {
-              const float g = dither_term(v[i], d2) * sgn;
-              if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] += g;
-            }
-          }
-        }
-      }
-    }
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) sum += x[n1];
-  float mean = 0.f;
-  if (p.remove_dc) mean = group_sum(sum, G::R2) * (1.0f / (float)Nw);
-  if (p.use_energy) {
-    float e = 0.f;
-#pragma unroll
-    for (int n1 = 0; n1 < F::NROW; ++n1) {
-      const float d = row_valid<NFFT, NW>(n1, n2, Nw) ? x[n1] - mean : 0.f;
-      e = fmaf(d, d, e);
-    }
-    e = group_sum(e, G::R2);
-    if (n2 == 0) *energy_slot = fast_log(fmaxf(e, kEps));
-  }
-  const float c = p.preemph;
-  const float mu = (1.0f - c) * mean;
-  [[maybe_unused]] float rot_prev = 0.f;  // NOISE: row n1 - 1 rotated by one lane (lane 0 <- lane R2 - 1)
-#pragma unroll
-  for (int n1 = 0; n1 < F::NROW; ++n1) {
-    float prev;
-    if constexpr (NOISE) {
-      // previous sample of the noisy frame: the neighbouring lane's x[n1], and for lane 0 the last
-      // lane's x[n1 - 1] -- which is what lane 0 received from the previous row's rotation
-      const float rot = __shfl_sync(0xffffffffu, x[n1], (n2 + G::R2 - 1) & (G::R2 - 1), G::R2);
-      const float wrap = n1 == 0 ? x[0] : rot_prev;  // j == 0: replicate padding (kaldi_signal.py:192-193)
-      prev = (n2 == 0) ? wrap : rot;
-      rot_prev = rot;
-    } else {
-      const int j = G::R2 * n1 + n2;
-      prev = (n1 == 0 && n2 == 0) ? x[0] : fr[(row_valid<NFFT, NW>(n1, n2, Nw) ? j : 1) - 1];
-    }
-    const bool rv = row_valid<NFFT, NW>(n1, n2, Nw);
-    const float wj = rv ? win[G::R2 * n1 + n2] : 0.f;
-    z[n1] = (fmaf(-c, prev, x[n1]) - mu) * wj;
-  }
-#pragma unroll
-  for (int n1 = F::NROW; n1 < 16; ++n1) z[n1] = 0.f;
-  (void)valid;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Two frames at once in the packed stage-1 layout: z[n1] = (frame A sample, frame B sample) of
 // j = R2 n1 + n2 after dither -> DC removal -> (raw log-energy) -> pre-emphasis -> window
@@ -180,7 +84,7 @@ __device__ __forceinline__ void load_frame_p(float (&z)[16], const FbankParams& 
 template <int NFFT, int NW, bool NOISE, typename ST>
 __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& p, const ST* frA, const ST* frB,
                                                 const float* win, float* energy_slots /*[2]*/, int n2, int b, int tA,
-                                                int tB, bool validA, bool validB) {
+                                                int tB, bool validA, bool validB, const float* nz_utt /*[T, Nw] or NULL*/) {
   using G = Geo<NFFT>;
   using F = FG<NFFT, NW>;
   const int Nw = F::kStatic ? NW : p.Nw;
@@ -191,42 +95,39 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
     x[n1] = c2_make(rv ? (float)frA[G::R2 * n1 + n2] : 0.f, rv ? (float)frB[G::R2 * n1 + n2] : 0.f);
   }
   if constexpr (NOISE) {
-    if (p.noise != nullptr) {  // parity mode: host-drawn rand_gauss, [B, T, Nw]
-      const float* nzA = p.noise + ((size_t)b * p.T + tA) * Nw;
-      const float* nzB = p.noise + ((size_t)b * p.T + tB) * Nw;
+    if (nz_utt != nullptr) {  // parity mode: host-drawn rand_gauss of this utterance, [T, Nw]
+      const float* nzA = nz_utt + (size_t)tA * Nw;
+      const float* nzB = nz_utt + (size_t)tB * Nw;
 #pragma unroll
       for (int n1 = 0; n1 < F::NROW; ++n1)
         if (row_valid<NFFT, NW>(n1, n2, Nw)) {
           const int j = G::R2 * n1 + n2;
           x[n1] = c2_fma(c2_make(validA ? __ldg(nzA + j) : 0.f, validB ? __ldg(nzB + j) : 0.f), c2_splat(p.dither), x[n1]);
         }
-    } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call)
-      const float d2 = p.dither * p.dither;
+    } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call); eight 16-bit uniforms per call
+      const float nk = 1.3862943611198906f * p.dither * p.dither;  // 2 ln 2 d^2
       const float sgn = p.dither < 0.f ? -1.f : 1.f;
 #pragma unroll
-      for (int c5 = 0; c5 * 5 < F::NROW; ++c5) {
-        const uint4 rA = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)tA, (uint32_t)b, 0x5eedu),
+      for (int c8 = 0; c8 * 8 < F::NROW; ++c8) {
+        const uint4 rA = philox4x32_7(make_uint4((uint32_t)(c8 * G::R2 + n2), (uint32_t)tA, (uint32_t)b, 0x5eedu),
                                       p.seed_lo, p.seed_hi);
-        const uint4 rB = philox4x32_7(make_uint4((uint32_t)(c5 * G::R2 + n2), (uint32_t)tB, (uint32_t)b, 0x5eedu),
+        const uint4 rB = philox4x32_7(make_uint4((uint32_t)(c8 * G::R2 + n2), (uint32_t)tB, (uint32_t)b, 0x5eedu),
                                       p.seed_lo, p.seed_hi);
-        const uint32_t vA[5] = {rA.x >> 8, rA.y >> 8, rA.z >> 8, rA.w >> 8,
-                                ((rA.x & 0xffu) << 16) | ((rA.y & 0xffu) << 8) | (rA.z & 0xffu)};
-        const uint32_t vB[5] = {rB.x >> 8, rB.y >> 8, rB.z >> 8, rB.w >> 8,
-                                ((rB.x & 0xffu) << 16) | ((rB.y & 0xffu) << 8) | (rB.z & 0xffu)};
+        const uint32_t wA[4] = {rA.x, rA.y, rA.z, rA.w}, wB[4] = {rB.x, rB.y, rB.z, rB.w};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int n1 = 5 * c5 + i;
+        for (int i = 0; i < 8; ++i) {
+          const int n1 = 8 * c8 + i;
           if (n1 < F::NROW) {
-            // dither * sqrt(-2 ln u) cos(2 pi u) for both frames; the MUFU ops are scalar, the rest packed
-            const float uA = (float)max(vA[i], 2u), uB = (float)max(vB[i], 2u);
-            const c2 a = c2_fma(c2_make(fast_log2(uA), fast_log2(uB)), c2_splat(-1.3862943611198906f * d2),
-                                c2_splat(33.27106466687737f * d2));
-            const c2 ang = c2_mul(c2_make(uA, uB), c2_splat(3.7450703370559213e-07f));  // 2 pi 2^-24
+            // d sqrt(-2 ln u) cos(2 pi u), u = (v + 1/2) 2^-16 (kaldi_signal.py:176-177 on a 16-bit grid) for both
+            // frames; the MUFU ops are scalar, the rest packed
+            const float uA = (float)((i & 1) ? (wA[i >> 1] >> 16) : (wA[i >> 1] & 0xffffu)) + 0.5f;
+            const float uB = (float)((i & 1) ? (wB[i >> 1] >> 16) : (wB[i >> 1] & 0xffffu)) + 0.5f;
+            const c2 a = c2_fma(c2_make(fast_log2(uA), fast_log2(uB)), c2_splat(-nk), c2_splat(16.0001f * nk));  // > 0
+            const c2 ang = c2_mul(c2_make(uA, uB), c2_splat(9.587379924285257e-05f));  // 2 pi 2^-16
             float csA, csB;
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csA) : "f"(c2_re(ang)));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(csB) : "f"(c2_im(ang)));
-            // clamp: the separately rounded products can leave a few ulps below zero at lg2 u == 24
-            const c2 g = c2_mul(c2_make(fast_sqrt(fmaxf(c2_re(a), 0.f)), fast_sqrt(fmaxf(c2_im(a), 0.f))), c2_make(csA, csB));
+            const c2 g = c2_mul(c2_make(fast_sqrt(c2_re(a)), fast_sqrt(c2_im(a))), c2_make(csA, csB));
             if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = c2_fma(g, c2_splat(sgn), x[n1]);  // sign of `dither`
           }
         }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [0] tables, [1 + w] samples of warp w
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int B = p.B, T = p.T, OP = L.op;
+  const int B = p.total_utts, OP = L.op;  // B: flattened utterances of all batches of the call
   TR(0);
 #ifdef SPL_TRACE
   if (lane == 0) {
@@ -126,6 +126,21 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
   double* wstat = reinterpret_cast<double*>(wr + L.st_off);  // fp64: sum x^2 - mean^2 must survive std << mean
   uint64_t* mybar = bars + 1 + w;
 
+  auto batch_of = [&](int u) -> int {  // batch of flattened utterance u (uniform loop over <= kMaxBatches descriptors)
+    int k = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.nb; ++i)
+      if (u >= p.bd[i].u0) k = i;
+    return k;
+  };
+  auto rows_before = [&](int u) -> long long {  // output rows of all utterances < u
+    long long rb = 0;
+    for (int k = 0; k < p.nb; ++k) {
+      const int cnt = u - p.bd[k].u0;
+      if (cnt > 0) rb += (long long)(cnt < p.bd[k].B ? cnt : p.bd[k].B) * p.bd[k].T;
+    }
+    return rb;
+  };
   // ---- 0. tables (one TMA bulk copy), group prefix (warp 0), barriers -----------------------------
   if (tid == 0) {
     mbar_init(bars, 1);
@@ -140,10 +155,11 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       const int bb = base + lane;
       int m = 0;
       if (bb < B) {
-        const long long n = p.wav_len[bb];
+        const UBatch& bd = p.bd[batch_of(bb)];
+        const long long n = bd.wav_len[bb - bd.u0];
         m = n >= Nw ? (int)(1 + (n - Nw) / S) : 0;  // kaldi_signal.py:90
-        m = m > T ? T : m;
-        if (blockIdx.x == 0 && p.feat_len) p.feat_len[bb] = m;
+        m = m > bd.T ? bd.T : m;
+        if (blockIdx.x == 0 && bd.feat_len) bd.feat_len[bb - bd.u0] = m;
       }
       const int gcount = (m + 3) >> 2;
       int incl = gcount, finc = m;
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       ctl[5] = g0;
       ctl[6] = 0;  // valid rows this CTA contributed to the global statistics
     } else {
-      const long long total_pad = (long long)B * T - fpre[B];
+      const long long total_pad = rows_before(B) - fpre[B];
       ctl[3] = share(total_pad, bid);
       ctl[4] = share(total_pad, bid + 1);
     }
@@ -210,9 +226,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
   const int g1 = ctl[1], b_first = ctl[2];
 
   // ---- per-warp helpers ---------------------------------------------------------------------------
-  const char* wav_lo = static_cast<const char*>(p.wav);
   constexpr int ES = (int)sizeof(ST);
-  const char* wav_hi = wav_lo + ((size_t)(B - 1) * p.wav_pitch + (size_t)p.wav_cols) * ES;
   int b_hint = b_first;
   auto fetch_group = [&]() {  // warp-uniform: next group id of this CTA (or >= g1)
     int g = 0;
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     return __shfl_sync(0xffffffffu, g, 0);
   };
   struct Grp {
-    int b, t0, n, head;
+    int b, t0, n, head, k;  // flattened utterance, first frame, frames, staged head elements, batch
     bool bulk;
   };
   // Locate group g and start staging its samples into `samp`.
@@ -229,6 +243,10 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     while (gpre[b + 1] <= g) ++b;
     b_hint = b;
     q.b = b;
+    q.k = batch_of(b);
+    const UBatch& bd = p.bd[q.k];
+    const char* wav_lo = static_cast<const char*>(bd.wav);
+    const char* wav_hi = wav_lo + ((size_t)(bd.B - 1) * bd.wav_pitch + (size_t)bd.wav_cols) * ES;
     q.t0 = 4 * (g - gpre[b]);
     const int left = (fpre[b + 1] - fpre[b]) - q.t0;
     q.n = left < 4 ? left : 4;
@@ -236,7 +254,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     q.bulk = false;
     q.head = 0;
     {
-      const char* src = wav_lo + ((size_t)b * p.wav_pitch + (size_t)q.t0 * S) * ES;
+      const char* src = wav_lo + ((size_t)(b - bd.u0) * bd.wav_pitch + (size_t)q.t0 * S) * ES;
       const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
       const int head = (int)((src - a0) / ES);  // 0..3 floats or 0..7 int16 before the first sample
       const uint32_t bytes = (uint32_t)(((head + need) * ES + 15) & ~15);
@@ -255,16 +273,18 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
   // per-utterance column sums (CMVN / SpecAug time means): running fp64 sums of this warp's current
   // utterance live in its own shared-memory rows; the CTA merges them once, after the loop
   int stat_b = -1, stat_rows = 0;
-  const bool want_stats = p.utt_stats != nullptr || p.global_stats != nullptr;
+  bool want_stats = p.global_stats != nullptr;
+  for (int k = 0; k < p.nb; ++k) want_stats = want_stats || p.bd[k].utt_stats != nullptr;
   auto flush_stats = [&]() {  // utterance change inside the loop (rare: a CTA's share spans 1-2 utterances)
     if (stat_b < 0) return;
     for (int c = lane; c < D_out; c += 32) {
       const double v1 = wstat[c], v2 = wstat[OP + c];
       wstat[c] = 0.0;
       wstat[OP + c] = 0.0;
-      if (p.utt_stats) {
-        atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 0) * D_out + c, v1);
-        atomicAdd(p.utt_stats + ((size_t)stat_b * 2 + 1) * D_out + c, v2);
+      const UBatch& sbd = p.bd[batch_of(stat_b)];
+      if (sbd.utt_stats) {
+        atomicAdd(sbd.utt_stats + ((size_t)(stat_b - sbd.u0) * 2 + 0) * D_out + c, v1);
+        atomicAdd(sbd.utt_stats + ((size_t)(stat_b - sbd.u0) * 2 + 1) * D_out + c, v2);
       }
       if (p.global_stats) {
         atomicAdd(p.global_stats + c, v1);
@@ -295,11 +315,14 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       parity ^= 1;
       TR(5 + 6 * tr_it);
     } else {  // warp-load staging (windows whose 16-byte envelope would leave the batch buffer)
-      const ST* src = static_cast<const ST*>(p.wav) + (size_t)cur.b * p.wav_pitch + (size_t)cur.t0 * S;
+      const UBatch& cbd = p.bd[cur.k];
+      const ST* src = static_cast<const ST*>(cbd.wav) + (size_t)(cur.b - cbd.u0) * cbd.wav_pitch + (size_t)cur.t0 * S;
       for (int i = lane; i < need; i += 32) samp[i] = __ldg(src + i);
       __syncwarp();
     }
     const ST* sbase = samp + cur.head;
+    const UBatch& gbd = p.bd[cur.k];
+    [[maybe_unused]] const float* nz_utt = gbd.noise ? gbd.noise + (size_t)(cur.b - gbd.u0) * gbd.T * Nw : nullptr;
     if (n < 4) {  // invalid frames must read finite data: zero everything past the valid span
       for (int i = need + lane; i < 3 * S + Nw; i += 32) samp[cur.head + i] = (ST)0;
       __syncwarp();
@@ -318,7 +341,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       }
       c2 z0[16], z1[16];
       load_frame_pair<NFFT, NW, NOISE, ST>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0, cur.t0 + 1, true,
-                                       n > 1);
+                                       n > 1, nz_utt);
       fft_dif_c<16, F::NROW>(z0);
       {
         float* er = e0 + n2 * G::EP;
@@ -331,7 +354,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
         }
       }
       load_frame_pair<NFFT, NW, NOISE, ST>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b, cur.t0 + 2,
-                                       cur.t0 + 3, n > 2, n > 3);
+                                       cur.t0 + 3, n > 2, n > 3, nz_utt);
       __syncwarp();  // every lane has its samples in registers: pair 1's planes may overwrite the buffer
       fft_dif_c<16, F::NROW>(z1);
       {
@@ -349,7 +372,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       const int fa = 2 * pr;
       c2 z[16];
       load_frame_pair<NFFT, NW, NOISE, ST>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
-                                       cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n);
+                                       cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n, nz_utt);
       __syncwarp();  // samples are in registers; pair 1's planes alias the buffer
       fft_dif_c<16, F::NROW>(z);
       float* er = (pr ? e1 : e0) + n2 * G::EP;
@@ -439,8 +462,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
 
     // ---- store the group's rows (contiguous in global memory) + column sums ----
     {
-      float* out_g = p.feats + ((size_t)cur.b * T + cur.t0) * D_out;
-      if ((D_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0)) {
+      float* out_g = gbd.feats + ((size_t)(cur.b - gbd.u0) * gbd.T + cur.t0) * D_out;
+      if ((D_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(gbd.feats) & 15) == 0)) {
         const int q = D_out >> 2;  // OP == D_out here: the rows are contiguous in shared memory too
         const float4* src = reinterpret_cast<const float4*>(orows);
         float4* dst = reinterpret_cast<float4*>(out_g);
@@ -513,20 +536,22 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     int q = q0 + (int)((long long)qn * w / kWWarps);
     const int q1 = q0 + (int)((long long)qn * (w + 1) / kWWarps);
     if (q < q1) {
-      int lo = 0, hi = B - 1;  // largest b with ppre(b) = b*T - fpre[b] <= q
+      int lo = 0, hi = B - 1;  // largest b with ppre(b) = rows_before(b) - fpre[b] <= q
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (mid * T - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+        if (rows_before(mid) - fpre[mid] <= q) lo = mid; else hi = mid - 1;
       }
       int b = lo;
-      const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0;
       while (q < q1) {
-        while ((b + 1) * T - fpre[b + 1] <= q) ++b;
+        while (b + 1 < B && rows_before(b + 1) - fpre[b + 1] <= q) ++b;
+        const UBatch& zbd = p.bd[batch_of(b)];
+        const int T = zbd.T;
+        const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(zbd.feats) & 15) == 0;
         const int m_b = fpre[b + 1] - fpre[b];
-        const int ofs = q - (b * T - fpre[b]);
+        const int ofs = q - (int)(rows_before(b) - fpre[b]);
         int nrows = (T - m_b) - ofs;
         nrows = nrows > q1 - q ? q1 - q : nrows;
-        float* dst = p.feats + ((size_t)b * T + m_b + ofs) * D_out;
+        float* dst = zbd.feats + ((size_t)(b - zbd.u0) * T + m_b + ofs) * D_out;
         if (vec) {
           float4* d4 = reinterpret_cast<float4*>(dst);
           const int n4 = nrows * (D_out >> 2);
@@ -568,7 +593,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
             any = true;
           }
         if (any) {
-          if (p.utt_stats) atomicAdd(p.utt_stats + ((size_t)b * 2 + which) * D_out + c, v);
+          const UBatch& mbd = p.bd[batch_of(b)];
+          if (mbd.utt_stats) atomicAdd(mbd.utt_stats + ((size_t)(b - mbd.u0) * 2 + which) * D_out + c, v);
           if (p.global_stats) atomicAdd(p.global_stats + which * D_out + c, v);
         }
       }

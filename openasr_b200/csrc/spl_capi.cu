@@ -48,7 +48,7 @@ struct spl_handle {
   int device;
   int D_out;
   int num_sms;
-  int engine;        // preferred kernel-A engine (SPL_ENGINE=umma|fft|simple; default umma)
+  int engine;        // preferred kernel-A engine (SPL_ENGINE=fft|umma|simple; default fft)
   bool fft_ok;       // the warp-pipelined FFT kernel fits this configuration
   size_t smem_warp;
   size_t smem_warp16;
@@ -265,10 +265,11 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   }
   h->num_sms = 148;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-  // SPL_ENGINE: umma (default: tcgen05 DFT-as-GEMM), fft (warp-pipelined FFT on the fp32x2 pipe), simple (one tile per CTA)
+  // SPL_ENGINE: fft (default: warp-pipelined FFT on the fp32x2 pipe -- the faster engine by measurement,
+  // profiles/r2_summary.md), umma (tcgen05 DFT-as-GEMM), simple (one tile per CTA, cross-check)
   const char* eng = std::getenv("SPL_ENGINE");
-  h->engine = ENGINE_UMMA;
-  if (eng && !std::strcmp(eng, "fft")) h->engine = ENGINE_FFT;
+  h->engine = ENGINE_FFT;
+  if (eng && !std::strcmp(eng, "umma")) h->engine = ENGINE_UMMA;
   if (eng && !std::strcmp(eng, "simple")) h->engine = ENGINE_SIMPLE;
   const char* cps = std::getenv("SPL_CTAS_PER_SM");  // FFT engine knob: 1 = 8-warp CTAs (two launches co-resident per SM)
   h->ctas_per_sm = (cps && cps[0] == '1') ? 1 : 2;
@@ -341,8 +342,12 @@ spl_fbank_args slice_batch(const spl_handle* h, const spl_fbank_args& a, int b0,
   return s;
 }
 
-cudaError_t launch_one_fft(spl_handle* h, const spl_fbank_args& a, cudaStream_t st, bool simple) {
+// FFT engines: `v[0..n)` share sample format / noise mode / global_stats; the warp-pipelined kernel takes them in
+// one launch (<= kMaxBatches batches, <= kMaxPersistentB utterances), the simple kernel one batch per launch
+cudaError_t launch_fft(spl_handle* h, const spl_fbank_args* v, int n, cudaStream_t st, bool simple) {
+  const spl_fbank_args& a = v[0];
   spl::FbankParams p;
+  std::memset(&p, 0, sizeof(p));
   p.S = h->cfg.window_shift;
   p.Nw = h->cfg.window_size;
   p.D = h->cfg.num_mel_bins;
@@ -366,6 +371,24 @@ cudaError_t launch_one_fft(spl_handle* h, const spl_fbank_args& a, cudaStream_t 
   p.utt_stats = a.utt_stats;
   p.global_stats = a.global_stats;
   p.tab = h->tab;
+  p.nb = n;
+  int u0 = 0;
+  for (int k = 0; k < n; ++k) {
+    spl::UBatch& bd = p.bd[k];
+    bd.wav = v[k].wav;
+    bd.wav_len = v[k].wav_len;
+    bd.feats = v[k].feats;
+    bd.feat_len = v[k].feat_len;
+    bd.noise = v[k].noise;
+    bd.utt_stats = v[k].utt_stats;
+    bd.wav_pitch = v[k].wav_pitch;
+    bd.wav_cols = v[k].wav_cols;
+    bd.B = v[k].B;
+    bd.T = v[k].T;
+    bd.u0 = u0;
+    u0 += v[k].B;
+  }
+  p.total_utts = u0;
   const bool with_noise = h->cfg.dither != 0.f;
   if (simple) return spl::launch_fbank(p, h->cfg.padded_size, with_noise, st);
   // one 16-warp CTA per SM; SPL_CTAS_PER_SM=1 (throughput mode) or a table block too large for 227 KB: 8-warp CTAs
@@ -463,22 +486,18 @@ int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n
     const spl_fbank_args& a = pieces[i];
     const int f = a.sample_format == SPL_SAMPLES_F32 ? 0 : 1;
     const bool umma = h->engine == ENGINE_UMMA && h->umma_ok[f];
+    const bool simple = !umma && (h->engine == ENGINE_SIMPLE || !h->fft_ok);
     cudaError_t e;
-    if (umma) {
-      size_t j = i + 1;
-      int utts = a.B;
-      while (j < pieces.size() && j - i < (size_t)spl::kMaxBatches && utts + pieces[j].B <= spl::kMaxUmmaUtts &&
-             pieces[j].sample_format == a.sample_format && (pieces[j].noise != nullptr) == (a.noise != nullptr) &&
-             pieces[j].global_stats == a.global_stats) {
-        utts += pieces[j].B;
-        ++j;
-      }
-      e = launch_umma(h, pieces.data() + i, (int)(j - i), st);
-      i = j;
-    } else {
-      e = launch_one_fft(h, a, st, h->engine == ENGINE_SIMPLE || !h->fft_ok);
-      ++i;
+    size_t j = i + 1;
+    int utts = a.B;
+    while (!simple && j < pieces.size() && j - i < (size_t)spl::kMaxBatches && utts + pieces[j].B <= spl::kMaxUmmaUtts &&
+           pieces[j].sample_format == a.sample_format && (pieces[j].noise != nullptr) == (a.noise != nullptr) &&
+           pieces[j].global_stats == a.global_stats) {
+      utts += pieces[j].B;
+      ++j;
     }
+    e = umma ? launch_umma(h, pieces.data() + i, (int)(j - i), st) : launch_fft(h, pieces.data() + i, (int)(j - i), st, simple);
+    i = j;
     if (e != cudaSuccess) return fail_cuda(e, "spl_fbank_forward: launch");
     g_launches.fetch_add(1);
   }
@@ -524,6 +543,16 @@ int spl_debug_umma_acc(spl_handle* h, float* host_out, size_t n_floats) {
   const size_t n = std::min<size_t>(n_floats, 128 * 513);
   cudaError_t e = cudaMemcpy(host_out, h->debug_acc, n * sizeof(float), cudaMemcpyDeviceToHost);
   return e == cudaSuccess ? SPL_OK : fail_cuda(e, "spl_debug_umma_acc");
+}
+
+int spl_debug_dither_noise(spl_handle* h, float* out, int32_t B, int32_t T, uint64_t seed, void* stream) {
+  if (!h || !out || B < 1 || T < 1) return fail(SPL_ERR_INVALID_ARG, "spl_debug_dither_noise: bad argument");
+  DeviceGuard guard(h->device);
+  cudaError_t e = spl::launch_dither_noise(out, B, T, h->cfg.window_size, h->cfg.padded_size / 16, seed,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "spl_debug_dither_noise: launch");
+  g_launches.fetch_add(1);
+  return SPL_OK;
 }
 
 const char* spl_engine_name(const spl_handle* h, int32_t sample_format) {

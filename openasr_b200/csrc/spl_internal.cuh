@@ -38,6 +38,22 @@ struct Tables {
   int32_t nj;
 };
 
+constexpr int kMaxBatches = 16;     // batches per launch
+constexpr int kMaxUmmaUtts = 512;   // flattened utterances per launch (frame prefix table in shared memory)
+
+struct UBatch {  // one padded batch of a (multi-)call; device pointers
+  const void* wav;
+  const int64_t* wav_len;
+  float* feats;
+  int64_t* feat_len;
+  const float* noise;
+  double* utt_stats;
+  int64_t wav_pitch, wav_cols;
+  int32_t B, T;
+  int32_t u0;    // index of the batch's first utterance in the flattened list
+  int32_t pad_;
+};
+
 struct FbankParams {
   // config
   int32_t S, Nw, D, D_out, use_energy, remove_dc;
@@ -55,6 +71,9 @@ struct FbankParams {
   double* utt_stats;
   double* global_stats;
   Tables tab;
+  // warp-pipelined kernel: the call as a list of batches (nb >= 1; the single-batch fields above describe bd[0])
+  int32_t nb, total_utts;
+  UBatch bd[kMaxBatches];
 };
 
 constexpr int kMaxPostBatches = 8;
@@ -94,23 +113,7 @@ cudaError_t launch_conv0_relu(const float* x, const float* w, const float* bias,
                               cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
-// tcgen05 DFT-as-GEMM engine (fbank_umma.cu): persistent, multi-batch
-constexpr int kMaxBatches = 8;      // batches per launch
-constexpr int kMaxUmmaUtts = 512;   // flattened utterances per launch (frame prefix table in shared memory)
-
-struct UBatch {  // one padded batch of a (multi-)call; device pointers
-  const void* wav;
-  const int64_t* wav_len;
-  float* feats;
-  int64_t* feat_len;
-  const float* noise;
-  double* utt_stats;
-  int64_t wav_pitch, wav_cols;
-  int32_t B, T;
-  int32_t u0;    // index of the batch's first utterance in the flattened list
-  int32_t pad_;
-};
-
+// tcgen05 DFT-as-GEMM engine (fbank_umma.cu): persistent, multi-batch (UBatch, kMaxBatches above)
 struct UmmaParams {
   int32_t S, Nw, D_out, remove_dc;
   float preemph, dither;
@@ -140,6 +143,9 @@ struct UmmaHostTables {
   std::vector<float> tab[2];
 };
 void build_umma_tables(int nfft, int Nw, int D, const float* window, const float* mel_dense, UmmaHostTables& out);
+
+// device dither generator, sample by sample (debug_kernels.cu)
+cudaError_t launch_dither_noise(float* out, int B, int T, int Nw, int R2, uint64_t seed, cudaStream_t st);
 
 // tcgen05 building-block self-test (tc_selftest.cu)
 cudaError_t launch_tc_selftest_sw32(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);

@@ -177,9 +177,12 @@ def post_inplace(feats: torch.Tensor, feat_len: torch.Tensor, *, cmvn_mode: str 
                  norm_vars: bool = True, utt_stats: Optional[torch.Tensor] = None,
                  global_mean: Optional[torch.Tensor] = None, global_istd: Optional[torch.Tensor] = None,
                  mask_params: Optional[torch.Tensor] = None, n_freq: int = 0, n_time: int = 0,
+                 mask_uniforms: Optional[torch.Tensor] = None, freq_width: float = 0.0, time_width: float = 0.0,
                  handle: Optional["FbankHandle"] = None, stream_ptr: Optional[C.c_void_p] = None) -> None:
     """CMVN + SpecAug in place on a contiguous CUDA [B, T, D] fp32 tensor.  With ``handle`` the library
-    selects the handle's device itself (no Python device context needed)."""
+    selects the handle's device itself (no Python device context needed).  Masks: either resolved rectangles
+    (``mask_params`` int32 [B, F+T, 2]) or the ``2 (F+T) x B`` uniforms in the reference's draw order
+    (``mask_uniforms`` + widths), which kernel B resolves against the device ``feat_len`` itself."""
     _require_cuda(feats, "features")
     if feats.dtype != torch.float32 or not feats.is_contiguous():
         raise ValueError("features must be contiguous float32")
@@ -197,6 +200,9 @@ def post_inplace(feats: torch.Tensor, feat_len: torch.Tensor, *, cmvn_mode: str 
     a.n_freq_masks, a.n_time_masks = int(n_freq), int(n_time)
     a.mask_params = (mask_params if isinstance(mask_params, int) else mask_params.data_ptr()) \
         if mask_params is not None else None
+    if mask_uniforms is not None:
+        a.mask_uniforms = mask_uniforms if isinstance(mask_uniforms, int) else mask_uniforms.data_ptr()
+        a.freq_mask_width, a.time_mask_width = float(freq_width), float(time_width)
     if handle is not None:
         _capi.check(lib.spl_post_inplace(handle._h, C.byref(a), stream_ptr or _stream_ptr(feats.device)),
                     "spl_post_inplace")

@@ -1,0 +1,204 @@
+"""GPU: round-2 entry points -- several batches per launch (spl_forward_multi), sync-free device lengths, SpecAug
+resolved in kernel B from the uploaded uniforms, the device dither generator itself, and the multi-GPU pieces
+(NCCL all-reduce of the global-CMVN statistics, DataParallel replicas)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_oracle as fo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SA = {"freq_mask_num": 2, "freq_mask_width": 27, "time_mask_num": 2, "time_mask_width": 40}
+
+
+def make_layer(**kw):
+    from openasr_b200 import SPLayer
+    conf = {"feature_type": "fbank", "sample_rate": 16000, "num_mel_bins": 80, "use_energy": False, "dither": 0.0}
+    conf.update(kw)
+    return SPLayer(conf).cuda(), conf
+
+
+@pytest.mark.parametrize("engine", ["fft", "umma"])
+def test_forward_multi_equals_consecutive_forwards(monkeypatch, engine):
+    """K batches in one launch of each kernel == K forward calls: lengths, padding, CMVN, SpecAug rectangles
+    (same host RNG stream).  The FFT engine is bit-identical (batch position does not enter its arithmetic); the
+    tcgen05 engine scales / pivots per 8-frame group of the flattened frame list, so it agrees within the tolerance."""
+    monkeypatch.setenv("SPL_ENGINE", engine)
+    layer, conf = make_layer(cmvn="utterance", spec_aug=SA)
+    layer.train()
+    assert layer._handle(torch.device("cuda", 0)).engine_name() == engine
+    batches = [fo.synth_batch(5 + k, 3000, 60000, 16000, seed=50 + k) for k in range(4)]
+    torch.manual_seed(3)
+    single = [layer(w.cuda(), l) for w, l in batches]
+    torch.manual_seed(3)
+    multi = layer.forward_multi([(w.cuda(), l) for w, l in batches])
+    torch.cuda.synchronize()
+    assert layer._handle(torch.device("cuda", 0)).debug_status() == 0
+    for (fs, ls), (fm, lm), (w, l) in zip(single, multi, batches):
+        assert torch.equal(ls, lm) and fs.shape == fm.shape
+        assert torch.equal(fs == 0, fm == 0)
+        if engine == "fft":
+            assert torch.equal(fs, fm)
+        else:
+            # normalised features: errors scale with 1/sigma_d; masks identical (checked through the zero pattern
+            # of padding and exact equality of the mask-fill positions below)
+            assert (fs - fm).abs().max().item() < 2e-2 and (fs - fm).abs().mean().item() < 1e-4
+    # against the oracle with the same uniforms
+    torch.manual_seed(3)
+    for (fm, lm), (w, l) in zip(multi, batches):
+        uni = torch.rand(8, w.shape[0])
+        ref, rl = fo.splayer_forward(w, l.tolist(), conf, training=True, specaug_uniforms=uni)
+        assert torch.equal(lm.cpu(), rl)
+        d = (fm.cpu() - ref).abs()
+        assert d.max().item() < 3e-2 and d.mean().item() < 2e-4, (d.max().item(), d.mean().item())
+
+
+def test_sync_free_device_lengths_match_host_lengths():
+    """`sync_free`: CUDA lengths are never read back; T comes from the padded width (== longest utterance, as the
+    reference's collate guarantees) and the masks are resolved in kernel B -> identical to the host-length path."""
+    layer_h, conf = make_layer(cmvn="utterance", spec_aug=SA)
+    layer_d, _ = make_layer(cmvn="utterance", spec_aug=SA, sync_free=True)
+    layer_h.train()
+    layer_d.train()
+    w, l = fo.synth_batch(7, 2000, 40000, 16000, seed=9)
+    w = w[:, :int(l.max())].contiguous()
+    torch.manual_seed(4)
+    fh, lh = layer_h(w.cuda(), l)
+    torch.manual_seed(4)
+    fd, ld = layer_d(w.cuda(), l.cuda())
+    assert torch.equal(lh, ld) and torch.equal(fh, fd)
+
+
+def test_kernel_b_uniforms_equal_host_rectangles():
+    """SpecAug from uniforms (device-resolved against feat_len) == SpecAug from the host-resolved rectangles of
+    spl_specaug_rects, including the len < width quirk (negative starts, spill into padding rows)."""
+    from openasr_b200 import frontend
+    g = torch.Generator().manual_seed(2)
+    B, T, V = 9, 120, 80
+    flen = torch.tensor([120, 3, 17, 39, 40, 41, 80, 1, 119])
+    x = torch.randn(B, T, V, generator=g)
+    x = x * (torch.arange(T)[None, :, None] < flen[:, None, None])
+    conf = {"freq_mask_num": 2, "freq_mask_width": 27, "time_mask_num": 3, "time_mask_width": 40}
+    uni = torch.rand(10, B, generator=g)
+    rect = frontend.specaug_rectangles_c(uni.numpy(), flen.numpy(), T, V, conf)
+    a, b = x.clone().cuda(), x.clone().cuda()
+    fl = flen.cuda()
+    st = frontend.column_stats(a, fl)
+    frontend.post_inplace(a, fl, utt_stats=st, mask_params=torch.from_numpy(rect).cuda(), n_freq=2, n_time=3)
+    frontend.post_inplace(b, fl, utt_stats=st, mask_uniforms=uni.cuda().contiguous(), n_freq=2, n_time=3,
+                          freq_width=27.0, time_width=40.0)
+    assert torch.equal(a, b)
+    ref, _ = fo.spec_aug(x.clone(), flen, conf, uniforms=uni)
+    assert torch.allclose(a.cpu(), ref, atol=1e-5)
+    assert torch.equal(a.cpu() != x, ref != x)
+
+
+@pytest.mark.parametrize("engine", ["fft", "umma"])
+@pytest.mark.parametrize("dither", [0.7, 1.5, 3.0, -1.0])
+def test_device_dither_any_scale_is_finite(monkeypatch, engine, dither):
+    """sqrt of a slightly negative argument for dither values that are not powers of two."""
+    monkeypatch.setenv("SPL_ENGINE", engine)
+    layer, conf = make_layer(dither=dither, cmvn="utterance")
+    layer.eval()
+    w, l = fo.synth_batch(16, 30000, 60000, 16000, seed=77)
+    for it in range(6):
+        torch.manual_seed(it)
+        f, _ = layer(w.cuda(), l)
+        assert torch.isfinite(f).all()
+
+
+def test_device_dither_noise_itself():
+    """The device generator, sample by sample (spl_debug_dither_noise): distribution of the reference's one-uniform
+    pseudo Box-Muller (kaldi_signal.py:176-177: mean 0.0576, std 1.057, range (-1.21, 5.6)), no correlation along
+    the frame, none between the overlapping samples of consecutive frames (the reference draws (m, Nw) fresh
+    values), and -- replayed through the host-noise mode -- the same features as the device-RNG mode."""
+    from openasr_b200 import _capi
+    layer, conf = make_layer(dither=1.0)
+    layer.eval()
+    dev = torch.device("cuda", 0)
+    h = layer._handle(dev)
+    assert h.engine_name() == "fft"
+    w, l = fo.synth_batch(6, 30000, 50000, 16000, seed=5)
+    frames = [fo.num_frames(int(n), 400, 160) for n in l.tolist()]
+    T = max(frames)
+    seed = 0x1234567812345678
+    noise = torch.empty((6, T, 400), device=dev)
+    _capi.check(h._lib.spl_debug_dither_noise(h._h, C.c_void_p(noise.data_ptr()), 6, T, seed,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "noise")
+    g = noise.cpu().double()
+    ref = fo.dither_noise((2000, 400), generator=torch.Generator().manual_seed(0)).double()
+    assert abs(g.mean().item() - ref.mean().item()) < 5e-3 and abs(g.mean().item() - 0.0576) < 5e-3
+    assert abs(g.std().item() - ref.std().item()) < 5e-3 and abs(g.std().item() - 1.057) < 5e-3
+    assert -1.22 < g.min().item() < -1.19 and 4.0 < g.max().item() < 5.7
+    for q in (0.01, 0.1, 0.5, 0.9, 0.99):  # quantiles of the two samples agree
+        assert abs(torch.quantile(g.flatten()[:4_000_000], q).item() - torch.quantile(ref.flatten(), q).item()) < 2e-2
+    z = g - g.mean()
+    lag1 = (z[:, :, 1:] * z[:, :, :-1]).mean().item() / z.var().item()
+    assert abs(lag1) < 3e-3
+    # sample s of frame t is sample s - 160 of frame t + 1: the two noise values must be independent
+    cross = (z[:, :-1, 160:] * z[:, 1:, :240]).mean().item() / z.var().item()
+    assert abs(cross) < 3e-3
+    across_utt = (z[0] * z[1]).mean().item() / z.var().item()
+    assert abs(across_utt) < 3e-3
+    # replay: device RNG == host-noise mode fed with the dumped noise
+    ld = l.cuda()
+    f_dev, _ = h.fbank(w.cuda(), ld, T, dither_seed=seed)
+    f_host, _ = h.fbank(w.cuda(), ld, T, noise=noise)
+    assert (f_dev - f_host).abs().max().item() < 2e-4
+    # and the oracle with that noise
+    for i in (0, 3):
+        r = fo.fbank(w[i, :l[i]], 16000.0, 80, dither=1.0, noise=noise[i, :frames[i]].cpu())
+        d = (f_dev[i, :frames[i]].cpu() - r).abs()
+        assert (d <= 1e-3 + 1e-4 * r.abs() + 4e-3 * (d > 0)).all() and d.mean().item() < 2e-5
+
+
+def test_engine_switch_and_defaults(monkeypatch):
+    layer, _ = make_layer()
+    assert layer._handle(torch.device("cuda", 0)).engine_name() == "fft"   # default: faster by measurement
+    monkeypatch.setenv("SPL_ENGINE", "umma")
+    layer, _ = make_layer()
+    h = layer._handle(torch.device("cuda", 0))
+    assert h.engine_name() == "umma" and h.engine_name(torch.int16) == "umma"
+    layer, _ = make_layer(use_energy=True)
+    assert layer._handle(torch.device("cuda", 0)).engine_name() == "fft"   # energy column: FFT engine
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_global_cmvn_nccl_two_ranks(tmp_path):
+    """GlobalCmvn under torch.distributed / NCCL on 2 ranks: statistics accumulated in kernel A's epilogue on each
+    GPU, one all_reduce, mean / istd and the normalised features against the fp64 oracle."""
+    out = tmp_path / "nccl.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(ROOT, "tests", "nccl_cmvn_worker.py"), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    import json
+    res = json.load(open(out))
+    assert res["world"] == 2 and res["ok"], res
+    print("NCCL global CMVN:", res)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dataparallel_many_iterations():
+    """nn.DataParallel replicas share the module's attributes (one HostStager): 40 iterations -- more than the 16
+    slots of a ring -- on every GPU, results equal to the single-GPU module."""
+    n = torch.cuda.device_count()
+    layer, conf = make_layer(cmvn="utterance", spec_aug=SA)
+    layer.train()
+    dp = torch.nn.DataParallel(layer, device_ids=list(range(n)))
+    w, l = fo.synth_batch(4 * n, 8000, 30000, 16000, seed=21)
+    for it in range(40):
+        f, fl = dp(w.cuda(0), l.cuda(0))
+        assert torch.isfinite(f).all() and fl.shape[0] == 4 * n
+    layer.eval()
+    f, fl = dp(w.cuda(0), l.cuda(0))
+    fr, flr = layer(w.cuda(0), l)
+    Tm = min(f.shape[1], fr.shape[1])
+    assert torch.equal(fl.cpu(), flr.cpu())

