@@ -487,7 +487,7 @@ def run_epoch(args, dev, rank, world, dist):
     stream = torch.cuda.Stream(device=dev)
     sp = C.c_void_p(stream.cuda_stream)
     gstats = torch.zeros(2 * h.d_out + 1, dtype=torch.float64, device=dev)
-    layer.set_global_cmvn(torch.zeros(h.d_out), torch.ones(h.d_out))  # buffers the pass-2 arguments point at
+    layer.set_global_cmvn(torch.zeros(h.d_out, device=dev), torch.ones(h.d_out, device=dev))  # buffers the pass-2 arguments point at
     # one graph = one walk over the pool; the passes replay it mine / pool times (+ a remainder graph)
     full, rem = divmod(mine, len(items))
     g1 = graph_of(make_groups(h, items, conf, layer, kb, len(items), 0, mode="stats", global_stats=gstats), stream)
