@@ -488,17 +488,32 @@ def run_epoch(args, dev, rank, world, dist):
     sp = C.c_void_p(stream.cuda_stream)
     gstats = torch.zeros(2 * h.d_out + 1, dtype=torch.float64, device=dev)
     layer.set_global_cmvn(torch.zeros(h.d_out, device=dev), torch.ones(h.d_out, device=dev))  # buffers the pass-2 arguments point at
+    # eager warm-up of both passes and of the collective (first launches configure the kernels, the first collective
+    # sets up NCCL's channels) BEFORE anything is captured; everything on `stream`
+    with torch.cuda.stream(stream):
+        for i, gr in enumerate(make_groups(h, items, conf, layer, kb, 2 * kb, 0, mode="stats", global_stats=gstats)):
+            gr.run(i, sp)
+        for i, gr in enumerate(make_groups(h, items, conf, layer, kb, 2 * kb, 0)):
+            gr.run(i, sp)
+    stream.synchronize()
+    if world > 1:
+        with torch.cuda.stream(stream):
+            dist.all_reduce(gstats.clone())
+        stream.synchronize()
     # one graph = one walk over the pool; the passes replay it mine / pool times (+ a remainder graph)
     full, rem = divmod(mine, len(items))
-    g1 = graph_of(make_groups(h, items, conf, layer, kb, len(items), 0, mode="stats", global_stats=gstats), stream)
-    g2 = graph_of(make_groups(h, items, conf, layer, kb, len(items), 0), stream)
-    g1r = graph_of(make_groups(h, items, conf, layer, kb, rem, 0, mode="stats", global_stats=gstats), stream) if rem else None
-    g2r = graph_of(make_groups(h, items, conf, layer, kb, rem, 0), stream) if rem else None
-    with torch.cuda.stream(stream):  # warm-up of both passes and of the collective
+    alive = []  # the groups own the per-utterance statistics buffers the captured launches write: keep them
+
+    def captured(n, mode):
+        alive.append(make_groups(h, items, conf, layer, kb, n, 0, mode=mode, global_stats=gstats if mode == "stats" else None))
+        return graph_of(alive[-1], stream)
+
+    g1, g2 = captured(len(items), "stats"), captured(len(items), "full")
+    g1r = captured(rem, "stats") if rem else None
+    g2r = captured(rem, "full") if rem else None
+    with torch.cuda.stream(stream):
         g1.replay()
         g2.replay()
-    if world > 1:
-        dist.all_reduce(gstats.clone())
     torch.cuda.synchronize(dev)
     gstats.zero_()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

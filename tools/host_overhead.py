@@ -26,6 +26,32 @@ for name, inp in (("fp32", xd), ("int16", xi)):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print("%s: host %.1f us/call (issue only), %.1f us/call incl. drain" % (name, 1e6 * (t1 - t0) / N, 1e6 * (t2 - t0) / N))
+# forward_multi: 8 batches per call (the per-call Python cost is paid once)
+batches = [(xd, lens_list)] * 8
+for _ in range(10):
+    layer.forward_multi(batches)
+torch.cuda.synchronize()
+N = 100
+t0 = time.perf_counter()
+for _ in range(N):
+    layer.forward_multi(batches)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print("forward_multi(8 batches): host %.1f us/call = %.1f us/batch (issue only)" % (1e6 * (t1 - t0) / N, 1e6 * (t1 - t0) / N / 8))
+# sync-free: CUDA lengths, T from the padded width
+conf_sf = dict(conf, sync_free=True)
+layer_sf = SPLayer(conf_sf).to(dev).train()
+xw = xd[:, :int(lens.max())].contiguous()
+ld = lens.to(dev)
+for _ in range(20):
+    layer_sf(xw, ld)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(300):
+    layer_sf(xw, ld)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print("sync_free forward (device lengths, no D2H): host %.1f us/call" % (1e6 * (t1 - t0) / 300))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(300):
