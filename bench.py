@@ -496,10 +496,14 @@ def run_epoch(args, dev, rank, world, dist):
         for i, gr in enumerate(make_groups(h, items, conf, layer, kb, 2 * kb, 0)):
             gr.run(i, sp)
     stream.synchronize()
-    if world > 1:
-        with torch.cuda.stream(stream):
-            dist.all_reduce(gstats.clone())
-        stream.synchronize()
+    with torch.cuda.stream(stream):  # also the torch ops of finalize (their first call loads / tunes kernels)
+        tmp = gstats.clone()
+        if world > 1:
+            dist.all_reduce(tmp)
+        m0, i0 = finalize_stats(tmp)
+        layer._gmean.copy_(m0.float())
+        layer._gistd.copy_(i0.float())
+    stream.synchronize()
     # one graph = one walk over the pool; the passes replay it mine / pool times (+ a remainder graph)
     full, rem = divmod(mine, len(items))
     alive = []  # the groups own the per-utterance statistics buffers the captured launches write: keep them
@@ -516,7 +520,7 @@ def run_epoch(args, dev, rank, world, dist):
         g2.replay()
     torch.cuda.synchronize(dev)
     gstats.zero_()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -529,6 +533,7 @@ def run_epoch(args, dev, rank, world, dist):
         ev[1].record(stream)
         if world > 1:
             dist.all_reduce(gstats)  # NCCL, on `stream` (the current stream): 2D+1 doubles over NVLink
+        ev[4].record(stream)
         mean, istd = finalize_stats(gstats)
         layer._gmean.copy_(mean.float())
         layer._gistd.copy_(istd.float())
@@ -542,14 +547,15 @@ def run_epoch(args, dev, rank, world, dist):
         dist.barrier()
     torch.cuda.synchronize(dev)
     ms = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
+    ms_ar = ev[1].elapsed_time(ev[4])
     audio = sum(items[i % len(items)]["audio_s"] for i in range(mine))
-    t = torch.tensor([sum(ms), ms[0], ms[1], ms[2], -audio], dtype=torch.float64, device=dev)
+    t = torch.tensor([sum(ms), ms[0], ms[1], ms[2], ms_ar], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ta = torch.tensor([audio], dtype=torch.float64, device=dev)
         dist.all_reduce(ta)
         audio = float(ta.item())
-    tot, p1, ar, p2 = [float(x) for x in t[:4]]
+    tot, p1, ar, p2, ar_only = [float(x) for x in t[:5]]
     count = float(gstats[2 * h.d_out].item())
     if rank != 0:
         return
@@ -562,7 +568,7 @@ def run_epoch(args, dev, rank, world, dist):
         "harness": {"pool_batches": len(items), "batches_per_launch": kb, "engine": h.engine_name(),
                     "partition": "epoch split evenly by batch over %d rank(s)" % world,
                     "collective": "one all_reduce(SUM) of %d fp64 (NCCL) between the passes" % (2 * h.d_out + 1) if world > 1 else "none (1 rank)"},
-        "epoch": {"audio_hours": audio / 3600.0, "pass1_stats_ms": p1, "allreduce_finalize_ms": ar, "pass2_features_ms": p2,
+        "epoch": {"audio_hours": audio / 3600.0, "pass1_stats_ms": p1, "allreduce_ms": ar_only, "allreduce_finalize_ms": ar, "pass2_features_ms": p2,
                   "total_ms": tot, "global_frames": count,
                   "pass1_audio_s_per_s": audio / (p1 * 1e-3), "pass2_audio_s_per_s": audio / (p2 * 1e-3)},
         "gpu_launches": (mine + kb - 1) // kb * 3, "peak_source": peak_src,
