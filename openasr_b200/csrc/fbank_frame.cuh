@@ -56,6 +56,16 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint32_t k0, uint32_t k
   return ctr;
 }
 
+// Table-driven dither: byte offset (entry * 4) of the f-th 12-bit field of one Philox result, ten fields per call --
+// two per word (bits 0..11, 12..23) and two more from the top bytes of word pairs (0, 1) and (2, 3).
+constexpr int kDithPerCall = 10;
+__device__ __forceinline__ uint32_t dith_off(const uint4& r, int f) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  constexpr uint32_t kMask = (uint32_t)(kDitherTab - 1) << 2;
+  if (f < 8) return ((f & 1) ? (w[f >> 1] >> 10) : (w[f >> 1] << 2)) & kMask;
+  return (__byte_perm(w[2 * (f - 8)], w[2 * (f - 8) + 1], 0x0073) << 2) & kMask;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Compile-time frame geometry: lane n2 of the stage-1 layout holds samples j = R2*n1 + n2.
 template <int NFFT, int NW>
@@ -81,10 +91,13 @@ __device__ __forceinline__ bool row_valid(int n1, int n2, int Nw) {
 // (kaldi_signal.py:174-199).  Frame A becomes the real part and frame B the imaginary part of the
 // complex FFT input, so every arithmetic step is one fp32x2 instruction for both frames.
 // ST: element type of the staged samples (float, or int16_t PCM converted at the first register load).
-template <int NFFT, int NW, bool NOISE, typename ST>
+// DTAB: the device-RNG noise comes from the shared-memory table `dtab` of d g(u_i) (12-bit uniforms: two shifts/masks,
+// one LDS and half a packed add per sample instead of three MUFU ops and a dozen ALU/FMA instructions).
+template <int NFFT, int NW, bool NOISE, typename ST, bool DTAB = false>
 __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& p, const ST* frA, const ST* frB,
                                                 const float* win, float* energy_slots /*[2]*/, int n2, int b, int tA,
-                                                int tB, bool validA, bool validB, const float* nz_utt /*[T, Nw] or NULL*/) {
+                                                int tB, bool validA, bool validB, const float* nz_utt /*[T, Nw] or NULL*/,
+                                                const float* dtab = nullptr) {
   using G = Geo<NFFT>;
   using F = FG<NFFT, NW>;
   const int Nw = F::kStatic ? NW : p.Nw;
@@ -104,7 +117,42 @@ __device__ __forceinline__ void load_frame_pair(c2 (&z)[16], const FbankParams& 
           const int j = G::R2 * n1 + n2;
           x[n1] = c2_fma(c2_make(validA ? __ldg(nzA + j) : 0.f, validB ? __ldg(nzB + j) : 0.f), c2_splat(p.dither), x[n1]);
         }
-    } else {  // throughput mode: counter-based stream keyed by (seed; b, t, n2, call); eight 16-bit uniforms per call
+    } else if constexpr (DTAB) {
+      // counter-based stream keyed by (seed; b, t, n2, call): ten 12-bit table draws per Philox call.  Rows 0..9 of a
+      // frame come from its own call; with NROW <= 15 the remaining rows of BOTH frames of the pair (tA even, tB = tA + 1)
+      // share a third call keyed by tA (fields 0..4 -> frame A, 5..9 -> frame B): 3 calls per pair instead of 4.
+      constexpr int kHead = F::NROW < kDithPerCall ? F::NROW : kDithPerCall;
+      const char* tb = reinterpret_cast<const char*>(dtab);
+      auto draw = [&](const uint4& rA, int fA, const uint4& rB, int fB) {
+        return c2_make(*reinterpret_cast<const float*>(tb + dith_off(rA, fA)),
+                       *reinterpret_cast<const float*>(tb + dith_off(rB, fB)));
+      };
+      {
+        const uint4 rA = philox4x32_7(make_uint4((uint32_t)n2, (uint32_t)tA, (uint32_t)b, 0x5eedu), p.seed_lo, p.seed_hi);
+        const uint4 rB = philox4x32_7(make_uint4((uint32_t)n2, (uint32_t)tB, (uint32_t)b, 0x5eedu), p.seed_lo, p.seed_hi);
+#pragma unroll
+        for (int n1 = 0; n1 < kHead; ++n1) {
+          const c2 g = draw(rA, n1, rB, n1);
+          if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = x[n1] + g;
+        }
+      }
+      if constexpr (F::NROW > kDithPerCall && F::NROW <= kDithPerCall + kDithPerCall / 2) {
+        const uint4 r = philox4x32_7(make_uint4((uint32_t)(G::R2 + n2), (uint32_t)tA, (uint32_t)b, 0x5eedu), p.seed_lo, p.seed_hi);
+#pragma unroll
+        for (int n1 = kDithPerCall; n1 < F::NROW; ++n1) {
+          const c2 g = draw(r, n1 - kDithPerCall, r, n1 - kDithPerCall + kDithPerCall / 2);
+          if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = x[n1] + g;
+        }
+      } else if constexpr (F::NROW > kDithPerCall) {
+        const uint4 rA = philox4x32_7(make_uint4((uint32_t)(G::R2 + n2), (uint32_t)tA, (uint32_t)b, 0x5eedu), p.seed_lo, p.seed_hi);
+        const uint4 rB = philox4x32_7(make_uint4((uint32_t)(G::R2 + n2), (uint32_t)tB, (uint32_t)b, 0x5eedu), p.seed_lo, p.seed_hi);
+#pragma unroll
+        for (int n1 = kDithPerCall; n1 < F::NROW; ++n1) {
+          const c2 g = draw(rA, n1 - kDithPerCall, rB, n1 - kDithPerCall);
+          if (row_valid<NFFT, NW>(n1, n2, Nw)) x[n1] = x[n1] + g;
+        }
+      }
+    } else {  // 8-warp variant (no room for the table): the formula on a 16-bit grid, eight uniforms per call
       const float nk = 1.3862943611198906f * p.dither * p.dither;  // 2 ln 2 d^2
       const float sgn = p.dither < 0.f ? -1.f : 1.f;
 #pragma unroll

@@ -52,7 +52,7 @@ struct WLayout {
   int en_off;    // 4 energy slots
   int st_off;    // this warp's running column sums of the current utterance: [2][op]
   int rw;        // region stride (multiple of 4)
-  int off_tab, off_gpre, off_fpre, off_ctl, off_bar, off_warp, total;
+  int off_tab, off_gpre, off_fpre, off_ppre, off_ctl, off_bar, off_warp, total;
 };
 
 __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words, int warps) {
@@ -69,7 +69,8 @@ __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_o
   L.off_tab = 0;
   L.off_gpre = wtab_words;
   L.off_fpre = L.off_gpre + kMaxPersistentB + 1;
-  L.off_ctl = (L.off_fpre + kMaxPersistentB + 1 + 3) & ~3;
+  L.off_ppre = L.off_fpre + kMaxPersistentB + 1;
+  L.off_ctl = (L.off_ppre + kMaxPersistentB + 1 + 3) & ~3;
   L.off_bar = (L.off_ctl + 8 + warps + 1) & ~1;  // ctl[8] + last utterance of every warp
   L.off_warp = (L.off_bar + 2 * (warps + 1) + 31) & ~31;
   L.total = L.off_warp + warps * L.rw;
@@ -88,11 +89,13 @@ size_t fbank_warp_smem_bytes(int nfft, int S, int Nw, int D_out, int wtab_words,
 template <int NFFT, int NW, bool NOISE, typename ST, int kWWarps>
 __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(const FbankParams p) {
   constexpr int kWThreads = kWWarps * 32;
+  constexpr bool kDTab = NOISE && kWWarps == 16;  // the 16-warp CTA has room for the dither table
   using G = Geo<NFFT>;
   using F = FG<NFFT, NW>;
   extern __shared__ __align__(128) float smem[];
   const int S = p.S, Nw = F::kStatic ? NW : p.Nw, D_out = p.D_out;
-  const WLayout L = make_wlayout(NFFT, S, Nw, D_out, p.tab.wtab_words, kWWarps);
+  const int tab_words = p.tab.wtab_words + (kDTab ? kDitherTab : 0);
+  const WLayout L = make_wlayout(NFFT, S, Nw, D_out, tab_words, kWWarps);
   static_assert(2 * G::PL >= 4 * G::PP, "power rows must fit in pair 0's exchange area");
   float* tab = smem + L.off_tab;
   const float4* melw = reinterpret_cast<const float4*>(tab);
@@ -100,8 +103,10 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
   const uint32_t* jinfo = reinterpret_cast<const uint32_t*>(tab + p.tab.wt_off_jinfo);
   const float* win = tab + p.tab.wt_off_win;
   const float* tws = tab + p.tab.wt_off_tw;
+  [[maybe_unused]] const float* dtab = tab + p.tab.wt_off_dith;
   int* gpre = reinterpret_cast<int*>(smem + L.off_gpre);  // gpre[b] = groups of utterances < b
   int* fpre = reinterpret_cast<int*>(smem + L.off_fpre);  // fpre[b] = frames of utterances < b
+  int* ppre = reinterpret_cast<int*>(smem + L.off_ppre);  // ppre[b] = zero-padding rows of utterances < b
   int* ctl = reinterpret_cast<int*>(smem + L.off_ctl);    // [0] next group ... [8 + w] last utterance of warp w
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [0] tables, [1 + w] samples of warp w
 
@@ -146,8 +151,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     mbar_init(bars, 1);
     for (int i = 0; i < kWWarps; ++i) mbar_init(bars + 1 + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bars, (uint32_t)p.tab.wtab_words * 4u);
-    bulk_g2s(tab, p.tab.wtab, (uint32_t)p.tab.wtab_words * 4u, bars);
+    mbar_expect_tx(bars, (uint32_t)tab_words * 4u);
+    bulk_g2s(tab, p.tab.wtab, (uint32_t)tab_words * 4u, bars);
   }
   if (w == 0) {
     int carry = 0, fcarry = 0;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       if (bb < B) {
         gpre[bb] = carry + incl - gcount;
         fpre[bb] = fcarry + finc - m;
+        ppre[bb] = (int)(rows_before(bb) - (fcarry + finc - m));
       }
       carry += __shfl_sync(0xffffffffu, incl, 31);
       fcarry += __shfl_sync(0xffffffffu, finc, 31);
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     if (lane == 0) {
       gpre[B] = carry;
       fpre[B] = fcarry;
+      ppre[B] = (int)(rows_before(B) - fcarry);
     }
   }
   for (int i = lane; i < 2 * OP; i += 32) wstat[i] = 0.0;
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       ctl[5] = g0;
       ctl[6] = 0;  // valid rows this CTA contributed to the global statistics
     } else {
-      const long long total_pad = rows_before(B) - fpre[B];
+      const long long total_pad = ppre[B];
       ctl[3] = share(total_pad, bid);
       ctl[4] = share(total_pad, bid + 1);
     }
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
 
   // ---- per-warp helpers ---------------------------------------------------------------------------
   constexpr int ES = (int)sizeof(ST);
-  int b_hint = b_first;
+  int b_hint = b_first, k_hint = 0;  // groups (hence utterances and batches) only move forward within a warp
   auto fetch_group = [&]() {  // warp-uniform: next group id of this CTA (or >= g1)
     int g = 0;
     if (lane == 0) g = atomicAdd(ctl, 1);
@@ -243,7 +250,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     while (gpre[b + 1] <= g) ++b;
     b_hint = b;
     q.b = b;
-    q.k = batch_of(b);
+    while (k_hint + 1 < p.nb && b >= p.bd[k_hint + 1].u0) ++k_hint;
+    q.k = k_hint;
     const UBatch& bd = p.bd[q.k];
     const char* wav_lo = static_cast<const char*>(bd.wav);
     const char* wav_hi = wav_lo + ((size_t)(bd.B - 1) * bd.wav_pitch + (size_t)bd.wav_cols) * ES;
@@ -340,8 +348,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
         twi[k1] = tws[NFFT + k1 * G::R2 + n2];
       }
       c2 z0[16], z1[16];
-      load_frame_pair<NFFT, NW, NOISE, ST>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0, cur.t0 + 1, true,
-                                       n > 1, nz_utt);
+      load_frame_pair<NFFT, NW, NOISE, ST, kDTab>(z0, p, sbase, sbase + S, win, energy + 0, n2, cur.b, cur.t0,
+                                                  cur.t0 + 1, true, n > 1, nz_utt, dtab);
       fft_dif_c<16, F::NROW>(z0);
       {
         float* er = e0 + n2 * G::EP;
@@ -353,8 +361,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
           ei[k1] = c2_im(o);
         }
       }
-      load_frame_pair<NFFT, NW, NOISE, ST>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b, cur.t0 + 2,
-                                       cur.t0 + 3, n > 2, n > 3, nz_utt);
+      load_frame_pair<NFFT, NW, NOISE, ST, kDTab>(z1, p, sbase + 2 * S, sbase + 3 * S, win, energy + 2, n2, cur.b,
+                                                  cur.t0 + 2, cur.t0 + 3, n > 2, n > 3, nz_utt, dtab);
       __syncwarp();  // every lane has its samples in registers: pair 1's planes may overwrite the buffer
       fft_dif_c<16, F::NROW>(z1);
       {
@@ -371,8 +379,8 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       const int pr = lane >> 4, n2 = lane & 15;
       const int fa = 2 * pr;
       c2 z[16];
-      load_frame_pair<NFFT, NW, NOISE, ST>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
-                                       cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n, nz_utt);
+      load_frame_pair<NFFT, NW, NOISE, ST, kDTab>(z, p, sbase + fa * S, sbase + (fa + 1) * S, win, energy + fa, n2, cur.b,
+                                                  cur.t0 + fa, cur.t0 + fa + 1, fa < n, fa + 1 < n, nz_utt, dtab);
       __syncwarp();  // samples are in registers; pair 1's planes alias the buffer
       fft_dif_c<16, F::NROW>(z);
       float* er = (pr ? e1 : e0) + n2 * G::EP;
@@ -536,19 +544,19 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     int q = q0 + (int)((long long)qn * w / kWWarps);
     const int q1 = q0 + (int)((long long)qn * (w + 1) / kWWarps);
     if (q < q1) {
-      int lo = 0, hi = B - 1;  // largest b with ppre(b) = rows_before(b) - fpre[b] <= q
+      int lo = 0, hi = B - 1;  // largest b with ppre[b] <= q
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (rows_before(mid) - fpre[mid] <= q) lo = mid; else hi = mid - 1;
+        if (ppre[mid] <= q) lo = mid; else hi = mid - 1;
       }
       int b = lo;
       while (q < q1) {
-        while (b + 1 < B && rows_before(b + 1) - fpre[b + 1] <= q) ++b;
+        while (b + 1 < B && ppre[b + 1] <= q) ++b;
         const UBatch& zbd = p.bd[batch_of(b)];
         const int T = zbd.T;
         const bool vec = (D_out & 3) == 0 && (reinterpret_cast<uintptr_t>(zbd.feats) & 15) == 0;
         const int m_b = fpre[b + 1] - fpre[b];
-        const int ofs = q - (int)(rows_before(b) - fpre[b]);
+        const int ofs = q - ppre[b];
         int nrows = (T - m_b) - ofs;
         nrows = nrows > q1 - q ? q1 - q : nrows;
         float* dst = zbd.feats + ((size_t)(b - zbd.u0) * T + m_b + ofs) * D_out;
@@ -613,7 +621,8 @@ extern "C" __attribute__((visibility("default"))) int spl_debug_trace(unsigned l
 // ---------------------------------------------------------------------------------------------
 template <int NFFT, int NW, bool NOISE, typename ST, int WARPS>
 static cudaError_t launch_w(const FbankParams& p, int num_ctas, cudaStream_t st) {
-  const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out, p.tab.wtab_words, WARPS);
+  const size_t smem = fbank_warp_smem_bytes(NFFT, p.S, NW > 0 ? NW : p.Nw, p.D_out,
+                                            p.tab.wtab_words + (NOISE && WARPS == 16 ? kDitherTab : 0), WARPS);
   static thread_local size_t configured[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);

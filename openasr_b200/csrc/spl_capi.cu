@@ -175,9 +175,10 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   const size_t wt_desc = pad4(ww.size()), wt_jinfo = wt_desc + pad4(wdesc.size()), wt_win = wt_jinfo + pad4(jinfo.size());
   const size_t wt_tw = wt_win + pad4(Nw), wt_words = wt_tw + 2 * (size_t)nfft;
+  const size_t wt_dith = wt_words, wt_end = wt_dith + spl::kDitherTab;  // dither table: staged only by the 16-warp variant
   spl::UmmaHostTables ut;
   if (!cfg->use_energy) spl::build_umma_tables(nfft, Nw, D, window, mel_dense, ut);
-  size_t n_items = wt_words + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
+  size_t n_items = wt_end + (size_t)Nw + 2 * (size_t)R2 * 16 + (size_t)(nnz > 0 ? nnz : 1) + 3 * (size_t)D;
   n_items = pad4(n_items);
   size_t o_utab[2] = {0, 0}, o_utw[2] = {0, 0};
   for (int f = 0; f < 2; ++f) {
@@ -200,12 +201,17 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
     std::memcpy(wt + wt_jinfo, jinfo.data(), jinfo.size() * 4);
     std::memcpy(wt + wt_win, window, Nw * 4);
     std::memcpy(wt + wt_tw, twt.data(), 2 * (size_t)nfft * 4);
+    float* dt = reinterpret_cast<float*>(wt + wt_dith);
+    for (int i = 0; i < spl::kDitherTab; ++i) {
+      const double u = ((double)i + 0.5) / (double)spl::kDitherTab;
+      dt[i] = (float)((double)cfg->dither * std::sqrt(-2.0 * std::log(u)) * std::cos(2.0 * M_PI * u));
+    }
   }
   for (int f = 0; f < 2; ++f) {
     if (!ut.tab[f].empty()) std::memcpy(host.data() + o_utab[f], ut.tab[f].data(), ut.tab[f].size() * 4);
     if (!ut.twiddles[f].empty()) std::memcpy(host.data() + o_utw[f], ut.twiddles[f].data(), ut.twiddles[f].size());
   }
-  size_t o = wt_words;
+  size_t o = wt_end;
   auto put = [&](const void* src, size_t n) {
     std::memcpy(host.data() + o, src, n * 4);
     size_t at = o;
@@ -247,6 +253,7 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   h->tab.wt_off_jinfo = (int32_t)wt_jinfo;
   h->tab.wt_off_win = (int32_t)wt_win;
   h->tab.wt_off_tw = (int32_t)wt_tw;
+  h->tab.wt_off_dith = (int32_t)wt_dith;
   h->tab.nj = nj;
   h->umma_nflush = ut.nflush;
   h->umma_nparts = ut.nparts;
@@ -274,7 +281,7 @@ int spl_create(const spl_config* cfg, const float* window, const float* mel_dens
   const char* cps = std::getenv("SPL_CTAS_PER_SM");  // FFT engine knob: 1 = 8-warp CTAs (two launches co-resident per SM)
   h->ctas_per_sm = (cps && cps[0] == '1') ? 1 : 2;
   h->smem_warp = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 8);
-  h->smem_warp16 = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_words, 16);
+  h->smem_warp16 = spl::fbank_warp_smem_bytes(nfft, S, Nw, h->D_out, (int)wt_end, 16);
   {  // the warp kernel stages a group's samples inside one pair's exchange planes
     const int pl = ((nfft / 16 * 17 + 15) / 32) * 32 + 16;
     h->fft_ok = h->smem_warp <= 113 * 1024 && 3 * S + Nw + 4 <= 2 * pl;
@@ -490,7 +497,10 @@ int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n
     cudaError_t e;
     size_t j = i + 1;
     int utts = a.B;
+    long long rows = (long long)a.B * a.T;  // row prefixes of one launch are 32-bit
+    if (rows > 0x7fffffffLL) return fail(SPL_ERR_UNSUPPORTED, "spl_fbank_forward: more than 2^31 - 1 output rows in 512 utterances");
     while (!simple && j < pieces.size() && j - i < (size_t)spl::kMaxBatches && utts + pieces[j].B <= spl::kMaxUmmaUtts &&
+           (rows += (long long)pieces[j].B * pieces[j].T) <= 0x7fffffffLL &&
            pieces[j].sample_format == a.sample_format && (pieces[j].noise != nullptr) == (a.noise != nullptr) &&
            pieces[j].global_stats == a.global_stats) {
       utts += pieces[j].B;
@@ -548,7 +558,11 @@ int spl_debug_umma_acc(spl_handle* h, float* host_out, size_t n_floats) {
 int spl_debug_dither_noise(spl_handle* h, float* out, int32_t B, int32_t T, uint64_t seed, void* stream) {
   if (!h || !out || B < 1 || T < 1) return fail(SPL_ERR_INVALID_ARG, "spl_debug_dither_noise: bad argument");
   DeviceGuard guard(h->device);
+  // the stream of the default configuration: the 16-warp FFT engine draws from the table, the 8-warp variant
+  // (SPL_CTAS_PER_SM=1) evaluates the formula on a 16-bit grid
+  const bool wide = h->ctas_per_sm == 2 && h->smem_warp16 <= 227 * 1024;
   cudaError_t e = spl::launch_dither_noise(out, B, T, h->cfg.window_size, h->cfg.padded_size / 16, seed,
+                                           wide ? h->tab.wtab + h->tab.wt_off_dith : nullptr, h->cfg.dither,
                                            static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "spl_debug_dither_noise: launch");
   g_launches.fetch_add(1);

@@ -35,9 +35,13 @@ struct Tables {
   const float* wtab;
   int32_t wtab_words;
   int32_t wt_off_desc, wt_off_jinfo, wt_off_win, wt_off_tw;
+  // dither table (16-warp variant): kDitherTab values d * g(u_i), u_i = (i + 1/2) / kDitherTab, of the reference's
+  // one-uniform transform g(u) = sqrt(-2 ln u) cos(2 pi u) (kaldi_signal.py:176-177), right after the block above
+  int32_t wt_off_dith;
   int32_t nj;
 };
 
+constexpr int kDitherTab = 4096;   // entries of the dither table (12-bit uniforms)
 constexpr int kMaxBatches = 16;     // batches per launch
 constexpr int kMaxUmmaUtts = 512;   // flattened utterances per launch (frame prefix table in shared memory)
 
@@ -145,7 +149,8 @@ struct UmmaHostTables {
 void build_umma_tables(int nfft, int Nw, int D, const float* window, const float* mel_dense, UmmaHostTables& out);
 
 // device dither generator, sample by sample (debug_kernels.cu)
-cudaError_t launch_dither_noise(float* out, int B, int T, int Nw, int R2, uint64_t seed, cudaStream_t st);
+cudaError_t launch_dither_noise(float* out, int B, int T, int Nw, int R2, uint64_t seed, const float* dtab, float dither,
+                                cudaStream_t st);
 
 // tcgen05 building-block self-test (tc_selftest.cu)
 cudaError_t launch_tc_selftest_sw32(const float* A, const float* B, float* D, int N, int K, int* status, cudaStream_t st);

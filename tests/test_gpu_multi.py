@@ -125,12 +125,12 @@ def test_device_dither_noise_itself():
     dev = torch.device("cuda", 0)
     h = layer._handle(dev)
     assert h.engine_name() == "fft"
-    w, l = fo.synth_batch(6, 30000, 50000, 16000, seed=5)
+    w, l = fo.synth_batch(16, 50000, 80000, 16000, seed=5)   # ~1.5 M overlapping pairs: 1 sigma of a correlation = 8e-4
     frames = [fo.num_frames(int(n), 400, 160) for n in l.tolist()]
     T = max(frames)
     seed = 0x1234567812345678
-    noise = torch.empty((6, T, 400), device=dev)
-    _capi.check(h._lib.spl_debug_dither_noise(h._h, C.c_void_p(noise.data_ptr()), 6, T, seed,
+    noise = torch.empty((16, T, 400), device=dev)
+    _capi.check(h._lib.spl_debug_dither_noise(h._h, C.c_void_p(noise.data_ptr()), 16, T, seed,
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "noise")
     g = noise.cpu().double()
     ref = fo.dither_noise((2000, 400), generator=torch.Generator().manual_seed(0)).double()
