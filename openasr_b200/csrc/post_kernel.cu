@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
   __shared__ __align__(16) float s_istd[kMaxDm];
   __shared__ __align__(16) float s_tm[kMaxDm];
   __shared__ int s_mask[2 * kMaxMasks];
+  __shared__ unsigned char s_rowtm[kPostRows];  // row t0 + r lies inside a time mask
   // blockIdx.y = flattened utterance over the batches of the call
   int kb = 0;
 #pragma unroll 1
@@ -80,6 +81,11 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
     t_hi = e > t_hi ? e : t_hi;
   }
   if (t0 >= t_hi) return;
+  if (tid < kPostRows) {  // time-mask membership once per row (not once per lane and row)
+    bool tmask = false;
+    for (int j = p.n_freq; j < nmask; ++j) tmask |= (t0 + tid >= s_mask[2 * j] && t0 + tid < s_mask[2 * j + 1]);
+    s_rowtm[tid] = tmask ? 1 : 0;
+  }
 
   if (tid < Dm) {
     const int d = tid;
@@ -106,6 +112,21 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
   const bool need_fm = p.n_freq > 0 && nmask > 0;
   constexpr int kWarpsB = kPostThreads / 32;
   constexpr int RB = 4;  // rows in flight per warp: their loads are issued together (one L2 round trip, not four)
+  float* const cta_rows = feats + ((size_t)b * T + t0) * Dm;  // row t of this CTA: cta_rows + (t - t0) * Dm
+  // frequency masks of this lane's columns, resolved once: bit 4 i + e <-> element e of float4 group lane + 32 i
+  [[maybe_unused]] uint32_t fbits = 0;
+  if (VEC4 && need_fm) {
+    for (int j = 0; j < p.n_freq; ++j) {
+      const int f0 = s_mask[2 * j], f1 = s_mask[2 * j + 1];
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = 4 * (lane + 32 * i) + e;
+          if (d >= f0 && d < f1) fbits |= 1u << (4 * i + e);
+        }
+    }
+  }
   for (int tb = t0 + w; tb < tend; tb += RB * kWarpsB) {
     if (VEC4) {
       // Dm % 4 == 0, rows 16-byte aligned: lane handles float4 groups lane (+ 32 when NG == 2)
@@ -115,11 +136,11 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int t = tb + r * kWarpsB;
-        bool tmask = false;
-        for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
-        tm[r] = tmask && t < tend;
-        live[r] = t < tend && !tmask && t < len;  // padding stays exactly 0 (freq means of a zero row are 0)
-        const float4* row4 = reinterpret_cast<const float4*>(feats + ((size_t)b * T + t) * Dm);
+        const bool in = t < tend;
+        const bool tmask = in && s_rowtm[in ? t - t0 : 0] != 0;
+        tm[r] = tmask;
+        live[r] = in && !tmask && t < len;  // padding stays exactly 0 (freq means of a zero row are 0)
+        const float4* row4 = reinterpret_cast<const float4*>(cta_rows + (t - t0) * Dm);
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
           const int g = lane + 32 * i;
@@ -129,17 +150,21 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
       }
       float sum[RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        sum[r] = 0.f;
+      for (int i = 0; i < NG; ++i) {
+        const int g = lane + 32 * i;
+        if (g < q) {
+          const float4 m = reinterpret_cast<const float4*>(s_mean)[g], sd = reinterpret_cast<const float4*>(s_istd)[g];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          const int g = lane + 32 * i;
-          if (g < q) {
-            const float4 m = reinterpret_cast<const float4*>(s_mean)[g], sd = reinterpret_cast<const float4*>(s_istd)[g];
+          for (int r = 0; r < RB; ++r) {
             float4& v = x[r][i];
             v = make_float4((v.x - m.x) * sd.x, (v.y - m.y) * sd.y, (v.z - m.z) * sd.z, (v.w - m.w) * sd.w);
-            sum[r] += (v.x + v.y) + (v.z + v.w);
+            const float part = (v.x + v.y) + (v.z + v.w);
+            sum[r] = i == 0 ? part : sum[r] + part;
           }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            if (i == 0) sum[r] = 0.f;
         }
       }
       if (need_fm) {
@@ -151,7 +176,7 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int t = tb + r * kWarpsB;
-        float4* row4 = reinterpret_cast<float4*>(feats + ((size_t)b * T + t) * Dm);
+        float4* row4 = reinterpret_cast<float4*>(cta_rows + (t - t0) * Dm);
         if (tm[r]) {  // may legitimately touch padding rows (reference quirk for len < width)
           for (int g = lane; g < q; g += 32) row4[g] = reinterpret_cast<const float4*>(s_tm)[g];
           continue;
@@ -162,14 +187,13 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
         for (int i = 0; i < NG; ++i) {
           const int g = lane + 32 * i;
           if (g < q) {
-            float v[4] = {x[r][i].x, x[r][i].y, x[r][i].z, x[r][i].w};
-            for (int j = 0; j < p.n_freq && j < nmask; ++j) {
-              const int f0 = s_mask[2 * j], f1 = s_mask[2 * j + 1];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (4 * g + e >= f0 && 4 * g + e < f1) v[e] = fm;
-            }
-            row4[g] = make_float4(v[0], v[1], v[2], v[3]);
+            float4 v = x[r][i];
+            const uint32_t fb = fbits >> (4 * i);
+            if (fb & 1u) v.x = fm;
+            if (fb & 2u) v.y = fm;
+            if (fb & 4u) v.z = fm;
+            if (fb & 8u) v.w = fm;
+            row4[g] = v;
           }
         }
       }
@@ -177,9 +201,8 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
       for (int r = 0; r < RB; ++r) {
         const int t = tb + r * kWarpsB;
         if (t >= tend) break;
-        float* row = feats + ((size_t)b * T + t) * Dm;
-        bool tmask = false;
-        for (int j = p.n_freq; j < nmask; ++j) tmask |= (t >= s_mask[2 * j] && t < s_mask[2 * j + 1]);
+        float* row = cta_rows + (t - t0) * Dm;
+        const bool tmask = s_rowtm[t - t0] != 0;
         if (tmask) {
           for (int d = lane; d < Dm; d += 32) row[d] = s_tm[d];
           continue;
