@@ -286,6 +286,35 @@ def test_full_training_forward_c2_like():
           fo.splayer_forward(x, lens.tolist(), conf, training=False, dtype=torch.float64)[0], scale=scale)
 
 
+@pytest.mark.parametrize("sr,D,B,lo,hi,tw", [(16000, 80, 32, 56000, 104000, 40), (8000, 40, 64, 16000, 48000, 40),
+                                             (16000, 80, 16, 192000, 320000, 100)])
+def test_full_batch_training_forward_vs_oracle(sr, D, B, lo, hi, tw):
+    """BASELINE configs[1..3] at their FULL batch size: fbank + utterance CMVN + SpecAug (training) against the oracle
+    (fp32 and fp64) with the same host uniforms -- every element of the batch, exact lengths, exact zero padding,
+    identical mask rectangles."""
+    sa = {"freq_mask_num": 2, "freq_mask_width": 27 if D == 80 else 13, "time_mask_num": 2, "time_mask_width": tw}
+    layer, conf = make_layer(sample_rate=sr, num_mel_bins=D, cmvn="utterance", spec_aug=sa)
+    layer.train()
+    x, lens = fo.synth_batch(B, lo, hi, sr, seed=4321)
+    torch.manual_seed(11)
+    feats, flen = layer(x.cuda(), lens)
+    torch.manual_seed(11)
+    uni = torch.rand(8, B)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni)
+    ref64, _ = fo.splayer_forward(x, lens.tolist(), conf, training=True, specaug_uniforms=uni, dtype=torch.float64)
+    assert torch.equal(flen.cpu(), rlen)
+    raw, _ = fo.splayer_forward(x, lens.tolist(), dict(conf, cmvn="none"), training=False)
+    istd = torch.stack([1.0 / raw[i, :m].std(0, unbiased=False) for i, m in enumerate(rlen.tolist())])
+    close(feats, ref, ref64, scale=istd.clamp_min(1.0)[:, None, :])
+    fc = feats.cpu()
+    for i, m in enumerate(rlen.tolist()):
+        assert torch.equal(fc[i, m:] == 0, ref[i, m:] == 0)
+    # the masked cells (rows replaced by time means, columns by frequency means) are the same cells
+    plain, _ = fo.splayer_forward(x, lens.tolist(), conf, training=False)
+    assert torch.equal((fc - plain).abs() > 1e-2, (ref - plain).abs() > 1e-2) or \
+        ((fc - plain).abs() > 1e-2).ne((ref - plain).abs() > 1e-2).sum().item() < 1e-5 * fc.numel()
+
+
 def test_short_time_mask_quirk():
     """len < time_mask_width: negative starts / spill into padding follow Python slice rules."""
     sa = {"freq_mask_num": 1, "freq_mask_width": 10, "time_mask_num": 2, "time_mask_width": 100}
