@@ -366,6 +366,16 @@ def measure_workload(args, wl, dev, rank, world, dist, want_e2e=True, shard=None
     out = {"value": value, "ms_total": ms_total, "launches": launches, "roofline": roofline,
            "pool_bytes": sum(it["wav"].numel() * 4 + it["feats"].numel() * 4 for it in items),
            "engine": h.engine_name()}
+    if want_e2e and world == 1 and kb > 1:  # one batch per launch: the per-step figure that is NOT amortised over kb batches
+        n1 = min(K, 64)
+        groups_1 = make_groups(h, items, conf, layer, 1, n1, W)
+        g1 = graph_of(groups_1, stream)
+        with torch.cuda.stream(stream):
+            g1.replay()
+        stream.synchronize()
+        ms_1 = time_graph(g1, stream, args.repeats, lambda: torch.cuda.synchronize(dev))
+        out["single_batch_launch"] = {"us_per_step": 1e3 * ms_1 / n1, "batches_per_launch": 1, "steps": n1,
+                                      "note": "kernel A + kernel B launched once per batch, same graph / pool hygiene"}
     if want_e2e:
         n_e2e = max(kb, min(K, args.e2e_steps) // kb * kb)
         out["copy_control"] = run_e2e(layer, items, dev, n_e2e, kb, world, dist, copy_only=True)
@@ -633,7 +643,8 @@ def run_ours(args):
                                  else "by utterance, %d rank(s), own pool per rank, no data-path collective" % world,
                     "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
         "roofline": res["roofline"], "cpu_baseline": cpu_baseline, "e2e": res["e2e"],
-        "e2e_int16": res["e2e_int16"], "copy_control": res["copy_control"], "secondary": secondary,
+        "e2e_int16": res["e2e_int16"], "copy_control": res["copy_control"],
+        "single_batch_launch": res.get("single_batch_launch"), "secondary": secondary,
         "gpu_launches": res["launches"], "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

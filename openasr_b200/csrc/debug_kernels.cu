@@ -13,7 +13,9 @@ namespace spl {
 __global__ void dither_noise_kernel(float* __restrict__ out, int B, int T, int Nw, int R2, uint32_t seed_lo, uint32_t seed_hi,
                                     const float* __restrict__ dtab, float inv_d) {
   const size_t n = (size_t)B * T * Nw;
-  const int nrow = (Nw + R2 - 1) / R2;
+  // rows per lane as the engine's template sees them: compiled-in window (400 @ 512, 200 @ 256) or the generic 16
+  const bool fixed = (R2 == 32 && Nw == 400) || (R2 == 16 && Nw == 200);
+  const int nrow = fixed ? (Nw + R2 - 1) / R2 : 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % Nw);
     const int t = (int)((i / Nw) % T), b = (int)(i / ((size_t)Nw * T));

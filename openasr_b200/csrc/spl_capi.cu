@@ -9,9 +9,16 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects itself
+
 #include "spl_internal.cuh"
 
 namespace {
+
+struct NvtxRange {  // shows kernel A / kernel B as named ranges in nsys / ncu timelines
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
@@ -462,6 +469,7 @@ int spl_fbank_forward_multi(spl_handle* h, const spl_fbank_args* args, int32_t n
   }
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_fbank_forward: cudaSetDevice failed");
+  NvtxRange range("spl:fbank (kernel A)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // zero the per-utterance sums (contiguous buffers of consecutive batches share one memset)
@@ -615,6 +623,7 @@ int spl_post_inplace_multi(spl_handle* h, const spl_post_args* args, int32_t n, 
   cudaGetDevice(&cur_dev);
   DeviceGuard guard(h ? h->device : cur_dev);
   if (!guard.ok) return fail(SPL_ERR_CUDA, "spl_post_inplace: cudaSetDevice failed");
+  NvtxRange range("spl:cmvn+specaug (kernel B)");
   for (int i0 = 0; i0 < n; i0 += spl::kMaxPostBatches) {
     spl::PostParams p;
     std::memset(&p, 0, sizeof(p));

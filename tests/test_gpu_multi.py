@@ -114,22 +114,26 @@ def test_device_dither_any_scale_is_finite(monkeypatch, engine, dither):
         assert torch.isfinite(f).all()
 
 
-def test_device_dither_noise_itself():
+@pytest.mark.parametrize("sr,D,dither", [(16000, 80, 1.0), (8000, 40, 1.0), (20000, 80, -0.5), (14000, 64, 2.0)])
+def test_device_dither_noise_itself(sr, D, dither):
     """The device generator, sample by sample (spl_debug_dither_noise): distribution of the reference's one-uniform
     pseudo Box-Muller (kaldi_signal.py:176-177: mean 0.0576, std 1.057, range (-1.21, 5.6)), no correlation along
     the frame, none between the overlapping samples of consecutive frames (the reference draws (m, Nw) fresh
-    values), and -- replayed through the host-noise mode -- the same features as the device-RNG mode."""
+    values), and -- replayed through the host-noise mode -- the same features as the device-RNG mode.  The four
+    cases cover the compiled-in windows (13 rows per lane: three Philox calls per frame pair), the generic-window
+    template with more than ten rows (20 kHz) and a negative / non-unit dither."""
     from openasr_b200 import _capi
-    layer, conf = make_layer(dither=1.0)
+    layer, conf = make_layer(dither=dither, sample_rate=sr, num_mel_bins=D)
     layer.eval()
     dev = torch.device("cuda", 0)
     h = layer._handle(dev)
     assert h.engine_name() == "fft"
-    w, l = fo.synth_batch(16, 50000, 80000, 16000, seed=5)   # ~1.5 M overlapping pairs: 1 sigma of a correlation = 8e-4
-    frames = [fo.num_frames(int(n), 400, 160) for n in l.tolist()]
+    win, shift = h.win, h.shift
+    w, l = fo.synth_batch(16, 50 * shift * 6, 80 * shift * 6, sr, seed=5)   # ~1.5 M overlapping pairs: 1 sigma = 8e-4
+    frames = [fo.num_frames(int(n), win, shift) for n in l.tolist()]
     T = max(frames)
     seed = 0x1234567812345678
-    noise = torch.empty((16, T, 400), device=dev)
+    noise = torch.empty((16, T, win), device=dev)
     _capi.check(h._lib.spl_debug_dither_noise(h._h, C.c_void_p(noise.data_ptr()), 16, T, seed,
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "noise")
     g = noise.cpu().double()
@@ -142,21 +146,61 @@ def test_device_dither_noise_itself():
     z = g - g.mean()
     lag1 = (z[:, :, 1:] * z[:, :, :-1]).mean().item() / z.var().item()
     assert abs(lag1) < 3e-3
-    # sample s of frame t is sample s - 160 of frame t + 1: the two noise values must be independent
-    cross = (z[:, :-1, 160:] * z[:, 1:, :240]).mean().item() / z.var().item()
-    assert abs(cross) < 3e-3
+    # sample s of frame t is sample s - shift of frame t + 1: the two noise values must be independent
+    cross = (z[:, :-1, shift:] * z[:, 1:, :win - shift]).mean().item() / z.var().item()
+    assert abs(cross) < 3.5e-3
     across_utt = (z[0] * z[1]).mean().item() / z.var().item()
-    assert abs(across_utt) < 3e-3
-    # replay: device RNG == host-noise mode fed with the dumped noise
+    assert abs(across_utt) < 4e-3
+    # rows of one lane (samples j and j + R2) come from different fields of the same Philox word
+    r2 = h.padded // 16
+    rows = (z[:, :, r2:] * z[:, :, :-r2]).mean().item() / z.var().item()
+    assert abs(rows) < 3e-3
+    # replay: device RNG == host-noise mode fed with the dumped noise (covers the sign and the scale of `dither`)
     ld = l.cuda()
     f_dev, _ = h.fbank(w.cuda(), ld, T, dither_seed=seed)
     f_host, _ = h.fbank(w.cuda(), ld, T, noise=noise)
-    assert (f_dev - f_host).abs().max().item() < 2e-4
+    assert (f_dev - f_host).abs().max().item() < 5e-4
     # and the oracle with that noise
     for i in (0, 3):
-        r = fo.fbank(w[i, :l[i]], 16000.0, 80, dither=1.0, noise=noise[i, :frames[i]].cpu())
+        r = fo.fbank(w[i, :l[i]], float(sr), D, dither=dither, noise=noise[i, :frames[i]].cpu())
         d = (f_dev[i, :frames[i]].cpu() - r).abs()
         assert (d <= 1e-3 + 1e-4 * r.abs() + 4e-3 * (d > 0)).all() and d.mean().item() < 2e-5
+
+
+def test_throughput_mode_eight_warp_ctas(monkeypatch):
+    """SPL_CTAS_PER_SM=1: the 8-warp variant of the FFT engine (two launches co-resident per SM).  Same features as
+    the oracle; its dither evaluates the formula on a 16-bit grid (no room for the table) -- same replay check."""
+    from openasr_b200 import _capi
+    monkeypatch.setenv("SPL_CTAS_PER_SM", "1")
+    layer, conf = make_layer(cmvn="utterance")
+    layer.eval()
+    x, lens = fo.synth_batch(7, 20000, 60000, 16000, seed=8)
+    feats, flen = layer(x.cuda(), lens)
+    ref, rlen = fo.splayer_forward(x, lens.tolist(), conf)
+    assert torch.equal(flen.cpu(), rlen)
+    d = (feats.cpu() - ref).abs()
+    assert d.max().item() < 3e-2 and d.mean().item() < 2e-4
+    monkeypatch.delenv("SPL_CTAS_PER_SM")
+    layer16, _ = make_layer(cmvn="utterance")
+    layer16.eval()
+    f16, _ = layer16(x.cuda(), lens)
+    assert torch.equal(f16, feats)  # same arithmetic per group whatever the CTA shape
+    monkeypatch.setenv("SPL_CTAS_PER_SM", "1")
+    layer_d, _ = make_layer(dither=1.0)
+    layer_d.eval()
+    h = layer_d._handle(torch.device("cuda", 0))
+    frames = [fo.num_frames(int(n), 400, 160) for n in lens.tolist()]
+    T = max(frames)
+    seed = 0x0123456789abcdef
+    noise = torch.empty((7, T, 400), device="cuda")
+    _capi.check(h._lib.spl_debug_dither_noise(h._h, C.c_void_p(noise.data_ptr()), 7, T, seed,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "noise")
+    g = noise.double()
+    assert abs(g.mean().item() - 0.0576) < 5e-3 and abs(g.std().item() - 1.057) < 5e-3 and g.max().item() > 4.3
+    ld = lens.cuda()
+    f_dev, _ = h.fbank(x.cuda(), ld, T, dither_seed=seed)
+    f_host, _ = h.fbank(x.cuda(), ld, T, noise=noise)
+    assert (f_dev - f_host).abs().max().item() < 5e-4
 
 
 def test_engine_switch_and_defaults(monkeypatch):
