@@ -363,6 +363,16 @@ def measure_workload(args, wl, dev, rank, world, dist, want_e2e=True, shard=None
                 "us_per_batch": 1e3 * ms_a / K, "batches_per_launch": kb,
                 "alg_bytes_per_launch": alg_bytes / len(groups_a),
                 "step_share": ms_a / ms_total if world == 1 else None}
+    # secondary ceiling: algorithmic fp32 flops of the path against the CUDA-core peak
+    nfft = 512 if sr > 8000 else 256
+    nw = int(sr * 0.025)
+    flops_per_frame = 2.5 * nfft * __import__("math").log2(nfft) + 5 * nw + 1.5 * nfft + 2.0 * nfft
+    frames = sum(float(items[(W + i) % len(items)]["flen"].sum().item()) for i in range(min(K, len(items)))) * (K / min(K, len(items)))
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flops x 1.965 GHz = 74.4 TFLOP/s
+    roofline["fp32_ceiling"] = {"flops_per_frame": float(flops_per_frame), "achieved": frames * flops_per_frame / (ms_a * 1e-3) / 1e12,
+                                "peak": fp32_peak, "unit": "TFLOP/s",
+                                "frac": frames * flops_per_frame / (ms_a * 1e-3) / 1e12 / fp32_peak,
+                                "note": "real FFT 2.5 N log2 N + framing 5 Nw + power 1.5 N + mel 2 N flops per frame; nominal CUDA-core peak"}
     out = {"value": value, "ms_total": ms_total, "launches": launches, "roofline": roofline,
            "pool_bytes": sum(it["wav"].numel() * 4 + it["feats"].numel() * 4 for it in items),
            "engine": h.engine_name()}
