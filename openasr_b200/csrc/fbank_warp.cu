@@ -52,7 +52,7 @@ struct WLayout {
   int en_off;    // 4 energy slots
   int st_off;    // this warp's running column sums of the current utterance: [2][op]
   int rw;        // region stride (multiple of 4)
-  int off_tab, off_gpre, off_fpre, off_ppre, off_ctl, off_bar, off_warp, total;
+  int off_tab, off_gpre, off_fpre, off_ppre, off_ctot, off_ctl, off_bar, off_warp, total;
 };
 
 __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_out, int wtab_words, int warps) {
@@ -70,7 +70,8 @@ __host__ __device__ inline WLayout make_wlayout(int nfft, int S, int Nw, int D_o
   L.off_gpre = wtab_words;
   L.off_fpre = L.off_gpre + kMaxPersistentB + 1;
   L.off_ppre = L.off_fpre + kMaxPersistentB + 1;
-  L.off_ctl = (L.off_ppre + kMaxPersistentB + 1 + 3) & ~3;
+  L.off_ctot = L.off_ppre + kMaxPersistentB + 1;
+  L.off_ctl = (L.off_ctot + 3 * (kMaxPersistentB / 32) + 3) & ~3;
   L.off_bar = (L.off_ctl + 8 + warps + 1) & ~1;  // ctl[8] + last utterance of every warp
   L.off_warp = (L.off_bar + 2 * (warps + 1) + 31) & ~31;
   L.total = L.off_warp + warps * L.rw;
@@ -138,14 +139,6 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
       if (u >= p.bd[i].u0) k = i;
     return k;
   };
-  auto rows_before = [&](int u) -> long long {  // output rows of all utterances < u
-    long long rb = 0;
-    for (int k = 0; k < p.nb; ++k) {
-      const int cnt = u - p.bd[k].u0;
-      if (cnt > 0) rb += (long long)(cnt < p.bd[k].B ? cnt : p.bd[k].B) * p.bd[k].T;
-    }
-    return rb;
-  };
   // ---- 0. tables (one TMA bulk copy), group prefix (warp 0), barriers -----------------------------
   if (tid == 0) {
     mbar_init(bars, 1);
@@ -154,45 +147,84 @@ __global__ void __launch_bounds__(kWWarps * 32, 16 / kWWarps) fbank_warp_kernel(
     mbar_expect_tx(bars, (uint32_t)tab_words * 4u);
     bulk_g2s(tab, p.tab.wtab, (uint32_t)tab_words * 4u, bars);
   }
-  if (w == 0) {
-    int carry = 0, fcarry = 0;
-    for (int base = 0; base < B; base += 32) {
-      const int bb = base + lane;
-      int m = 0;
-      if (bb < B) {
-        const UBatch& bd = p.bd[batch_of(bb)];
-        const long long n = bd.wav_len[bb - bd.u0];
-        m = n >= Nw ? (int)(1 + (n - Nw) / S) : 0;  // kaldi_signal.py:90
-        m = m > bd.T ? bd.T : m;
-        if (blockIdx.x == 0 && bd.feat_len) bd.feat_len[bb - bd.u0] = m;
-      }
-      const int gcount = (m + 3) >> 2;
-      int incl = gcount, finc = m;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        const int u = __shfl_up_sync(0xffffffffu, finc, o);
-        if (lane >= o) {
-          incl += v;
-          finc += u;
-        }
-      }
-      if (bb < B) {
-        gpre[bb] = carry + incl - gcount;
-        fpre[bb] = fcarry + finc - m;
-        ppre[bb] = (int)(rows_before(bb) - (fcarry + finc - m));
-      }
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-      fcarry += __shfl_sync(0xffffffffu, finc, 31);
+  // Prefix tables over the flattened utterances (groups, frames, zero-padding rows), in parallel: warp w scans the
+  // 32-utterance chunks w, w + warps, ... (one round of global loads for the whole CTA), the chunk totals are scanned
+  // by every warp after the barrier and added to its own entries.
+  constexpr int kChunks = kMaxPersistentB / 32;
+  static_assert(kChunks <= 32, "chunk totals are scanned by one warp");
+  int* ctot = reinterpret_cast<int*>(smem + L.off_ctot);  // [3][kChunks]
+  const int nchunk = (B + 31) >> 5;
+  for (int c = w; c < nchunk; c += kWWarps) {
+    const int bb = 32 * c + lane;
+    int m = 0, pad = 0;
+    if (bb < B) {
+      const UBatch& bd = p.bd[batch_of(bb)];
+      const long long n = bd.wav_len[bb - bd.u0];
+      m = n >= Nw ? (int)(1 + (n - Nw) / S) : 0;  // kaldi_signal.py:90
+      m = m > bd.T ? bd.T : m;
+      pad = bd.T - m;
+      if (blockIdx.x == 0 && bd.feat_len) bd.feat_len[bb - bd.u0] = m;
     }
-    if (lane == 0) {
-      gpre[B] = carry;
-      fpre[B] = fcarry;
-      ppre[B] = (int)(rows_before(B) - fcarry);
+    const int gcount = (m + 3) >> 2;
+    int ginc = gcount, finc = m, pinc = pad;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int vg = __shfl_up_sync(0xffffffffu, ginc, o);
+      const int vf = __shfl_up_sync(0xffffffffu, finc, o);
+      const int vp = __shfl_up_sync(0xffffffffu, pinc, o);
+      if (lane >= o) {
+        ginc += vg;
+        finc += vf;
+        pinc += vp;
+      }
+    }
+    if (bb < B) {  // chunk-local exclusive prefixes
+      gpre[bb] = ginc - gcount;
+      fpre[bb] = finc - m;
+      ppre[bb] = pinc - pad;
+    }
+    if (lane == 31) {
+      ctot[c] = ginc;
+      ctot[kChunks + c] = finc;
+      ctot[2 * kChunks + c] = pinc;
     }
   }
   for (int i = lane; i < 2 * OP; i += 32) wstat[i] = 0.0;
   TR(22);
+  __syncthreads();
+  {
+    const int og = lane < nchunk ? ctot[lane] : 0, of = lane < nchunk ? ctot[kChunks + lane] : 0,
+              op = lane < nchunk ? ctot[2 * kChunks + lane] : 0;
+    int ginc = og, finc = of, pinc = op;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int vg = __shfl_up_sync(0xffffffffu, ginc, o);
+      const int vf = __shfl_up_sync(0xffffffffu, finc, o);
+      const int vp = __shfl_up_sync(0xffffffffu, pinc, o);
+      if (lane >= o) {
+        ginc += vg;
+        finc += vf;
+        pinc += vp;
+      }
+    }
+    for (int c = w; c < nchunk; c += kWWarps) {  // exclusive chunk offsets of this warp's chunks
+      const int ag = __shfl_sync(0xffffffffu, ginc - og, c), af = __shfl_sync(0xffffffffu, finc - of, c),
+                ap = __shfl_sync(0xffffffffu, pinc - op, c);
+      const int bb = 32 * c + lane;
+      if (bb < B) {
+        gpre[bb] += ag;
+        fpre[bb] += af;
+        ppre[bb] += ap;
+      }
+    }
+    const int tg = __shfl_sync(0xffffffffu, ginc, nchunk - 1), tf = __shfl_sync(0xffffffffu, finc, nchunk - 1),
+              tp = __shfl_sync(0xffffffffu, pinc, nchunk - 1);
+    if (tid == 0) {
+      gpre[B] = tg;
+      fpre[B] = tf;
+      ppre[B] = tp;
+    }
+  }
   __syncthreads();
   TR(23);
   // This CTA's contiguous share of the group list (thread 0) and of the zero-padding rows (thread 32).
