@@ -266,13 +266,26 @@ def make_groups(h, items, conf, layer, kb, n_steps, start, mode="full", global_s
     return groups
 
 
-def graph_of(groups, stream, seed0=0x9E3779B97F4A7C15):
+def graph_of(groups, stream, seed0=0x9E3779B97F4A7C15, side=()):
+    """One CUDA graph of all groups.  side: extra streams forked inside the capture -- group i runs (kernel A then
+    kernel B) on lane i % (1 + len(side)), so that the launch of one group fills the tail of the previous one."""
     g = torch.cuda.CUDAGraph()
-    sp = C.c_void_p(stream.cuda_stream)
+    lanes = [stream] + list(side)
     with torch.cuda.stream(stream):
         with torch.cuda.graph(g, stream=stream):
+            if side:
+                fork = torch.cuda.Event()
+                fork.record(stream)
+                for s in side:
+                    s.wait_event(fork)
             for i, gr in enumerate(groups):
-                gr.run(seed0 + i, sp)
+                ln = lanes[i % len(lanes)]
+                with torch.cuda.stream(ln):
+                    gr.run(seed0 + i, C.c_void_p(ln.cuda_stream))
+            for s in side:
+                join = torch.cuda.Event()
+                join.record(s)
+                stream.wait_event(join)
     return g
 
 
@@ -329,7 +342,8 @@ def measure_workload(args, wl, dev, rank, world, dist, want_e2e=True, shard=None
     # timed graph on the pool positions that FOLLOW the warm-up (nothing of it is L2-warm: the pool is several
     # times the 126 MB L2 and is walked in order)
     groups = make_groups(h, items, conf, layer, kb, K, W)
-    g = graph_of(groups, stream)
+    side = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams) - 1)]
+    g = graph_of(groups, stream, side=side)
     with torch.cuda.stream(stream):
         g.replay()  # graph warm-up (its inputs are evicted again by the time the replay wraps around the pool)
     stream.synchronize()
@@ -647,7 +661,7 @@ def run_ours(args):
         "data": "synthetic", "config": public_config(wl, args.dither),
         "harness": {"engine": res["engine"], "dither_rng": "device", "pool_batches": args.pool, "pool_bytes": res["pool_bytes"],
                     "l2_flush": "pool larger than L2 (126 MB), walked in order; the timed steps follow the warm-up steps in the pool",
-                    "batches_per_launch": args.batches_per_launch, "cuda_graph": True,
+                    "batches_per_launch": args.batches_per_launch, "cuda_graph": True, "streams": args.streams,
                     "timing": "best of %d regions of K steps, CUDA events, amortised over %d batches per launch" % (args.repeats, args.batches_per_launch),
                     "partition": ("every batch sharded by utterance over %d ranks (strong scaling)" % world) if shard
                                  else "by utterance, %d rank(s), own pool per rank, no data-path collective" % world,
@@ -757,6 +771,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--e2e-steps", type=int, default=96)
+    ap.add_argument("--streams", type=int, default=1, help="launch lanes of the `value` graph (1 = strictly serial launches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()

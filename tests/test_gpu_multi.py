@@ -60,6 +60,36 @@ def test_forward_multi_equals_consecutive_forwards(monkeypatch, engine):
         assert d.max().item() < 3e-2 and d.mean().item() < 2e-4, (d.max().item(), d.mean().item())
 
 
+def test_large_launch_ten_full_batches():
+    """A launch of the size bench.py times (ten AISHELL-shaped batches, 40 k groups, every CTA's share spans several
+    utterances and batches): same features as batch-by-batch calls, bit for bit without CMVN (the arithmetic of a
+    group does not depend on which warp runs it), CMVN sums within fp64 rounding, repeated calls agree, padding exact."""
+    layer, conf = make_layer()
+    layer.eval()
+    batches = [fo.synth_batch(32, 56000, 104000, 16000, seed=900 + k) for k in range(10)]
+    dev_batches = [(w.cuda(), l) for w, l in batches]
+    single = [layer(w, l) for w, l in dev_batches]
+    multi = layer.forward_multi(dev_batches)
+    for (fs, ls), (fm, lm) in zip(single, multi):
+        assert torch.equal(ls, lm) and torch.equal(fs, fm)
+    for _ in range(5):
+        again = layer.forward_multi(dev_batches)
+        for (fm, lm), (fa, la) in zip(multi, again):
+            assert torch.equal(fm, fa) and torch.equal(lm, la)
+    w0, l0 = batches[9]   # the last batch of the launch against the oracle
+    ref, rl = fo.splayer_forward(w0[:4], l0[:4].tolist(), conf)
+    d = (multi[9][0][:4, :ref.shape[1]].cpu() - ref).abs()
+    assert d.max().item() < 1e-2 and d.mean().item() < 2e-5
+    layer_c, conf_c = make_layer(cmvn="utterance")
+    layer_c.eval()
+    sc = [layer_c(w, l) for w, l in dev_batches]
+    mc = layer_c.forward_multi(dev_batches)
+    for (fs, ls), (fm, lm) in zip(sc, mc):
+        assert torch.equal(ls, lm) and (fs - fm).abs().max().item() < 1e-4
+        for i, m in enumerate(lm.tolist()):
+            assert (fm[i, m:] == 0).all()
+
+
 def test_sync_free_device_lengths_match_host_lengths():
     """`sync_free`: CUDA lengths are never read back; T comes from the padded width (== longest utterance, as the
     reference's collate guarantees) and the masks are resolved in kernel B -> identical to the host-length path."""
