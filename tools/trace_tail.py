@@ -48,10 +48,9 @@ print("launch = %.0f cycles (%.1f us at 1.965 GHz); mean warp busy in the loop %
 print("  prologue share %.3f, tail after the warp's last group %.3f (intra-CTA %.3f + inter-CTA %.3f)" % (
     rel[:, :, 3].mean() / total, (total - loop_end).mean() / total,
     (cta_end[:, None] - loop_end).mean() / total, (total - cta_end).mean() / total))
-smid = t[:, 0, 29]
 order = np.argsort(cta_end)
 np.save(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "trace_tail_K%d_%s.npy" % (K, os.environ.get("TAG", "a"))),
-        np.stack([np.arange(NCTA), smid, cta_end, loop_end.mean(axis=1)]))
+        np.stack([np.arange(NCTA), cta_end, loop_end.mean(axis=1)]))
 print("correlation of CTA end with blockIdx: %.3f" % np.corrcoef(np.arange(NCTA), cta_end)[0, 1])
-print("fastest CTAs (end, sm):", [(int(cta_end[c]), int(smid[c])) for c in order[:5]])
-print("slowest CTAs (end, sm):", [(int(cta_end[c]), int(smid[c])) for c in order[-5:]])
+print("fastest CTAs (blockIdx, end):", [(int(c), int(cta_end[c])) for c in order[:5]])
+print("slowest CTAs (blockIdx, end):", [(int(c), int(cta_end[c])) for c in order[-5:]])

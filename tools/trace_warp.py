@@ -67,7 +67,7 @@ for it in range(4):
 print("groups per warp histogram:", np.bincount(its.ravel()))
 
 # per-SM view: which CTAs share an SM, when each SM finishes, and how many groups it ran
-smid = t[:, 0, 29]
+smid = t[:, 0, 26]
 gt0 = t[:, :, 1].min()
 cta_start_ns = t[:, :, 1].min(axis=1) - gt0
 cta_groups = its.sum(axis=1)
