@@ -24,13 +24,10 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
   __shared__ __align__(16) float s_tm[kMaxDm];
   __shared__ int s_mask[2 * kMaxMasks];
   __shared__ unsigned char s_rowtm[kPostRows];  // row t0 + r lies inside a time mask
-  // blockIdx.y = flattened utterance over the batches of the call
-  int kb = 0;
-#pragma unroll 1
-  for (int i = 1; i < p.nb; ++i)
-    if ((int)blockIdx.y >= p.bd[i].u0) kb = i;
-  const PostBatch& bd = p.bd[kb];
-  const int b = blockIdx.y - bd.u0, t0 = blockIdx.x * kPostRows;
+  // blockIdx.z = batch of the call, blockIdx.y = utterance within it (the grid covers the largest batch)
+  const PostBatch& bd = p.bd[blockIdx.z];
+  const int b = blockIdx.y, t0 = blockIdx.x * kPostRows;
+  if (b >= bd.B) return;
   const int T = bd.T;
   if (t0 >= T) return;
   float* const feats = bd.feats;
@@ -241,14 +238,14 @@ __global__ void __launch_bounds__(kPostThreads, 5) post_kernel(const PostParams 
 }
 
 cudaError_t launch_post(const PostParams& p, cudaStream_t st) {
-  int tmax = 1, utts = 0;
+  int tmax = 1, utts = 1;
   bool aligned = true;
   for (int k = 0; k < p.nb; ++k) {
     tmax = p.bd[k].T > tmax ? p.bd[k].T : tmax;
-    utts += p.bd[k].B;
+    utts = p.bd[k].B > utts ? p.bd[k].B : utts;
     aligned = aligned && (reinterpret_cast<uintptr_t>(p.bd[k].feats) & 15) == 0;
   }
-  dim3 grid((tmax + kPostRows - 1) / kPostRows, utts);
+  dim3 grid((tmax + kPostRows - 1) / kPostRows, utts, p.nb);
   const bool vec = (p.Dm & 3) == 0 && p.Dm <= 256 && aligned;
   if (vec && p.Dm <= 128)
     post_kernel<true, 1><<<grid, kPostThreads, 0, st>>>(p);
