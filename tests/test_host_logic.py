@@ -27,6 +27,36 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"null" in lib.spl_last_error()
 
 
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/spl_capi.h compiles as C99 and as C++17 (no torch / CUDA types in the signatures), and the ctypes
+    mirrors in openasr_b200/_capi.py have the size and field offsets the C compiler gives the structs."""
+    import shutil
+    import subprocess
+    from openasr_b200 import _capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "spl_capi.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    structs = {"spl_config": _capi.SplConfig, "spl_fbank_args": _capi.SplFbankArgs, "spl_post_args": _capi.SplPostArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "spl_capi.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_tables_bit_identical_to_oracle():
     from openasr_b200 import tables
     for sr in (16000.0, 8000.0, 11025.0):
